@@ -1,0 +1,1224 @@
+// Batched adaptive NUTS on the tilted densities of all sites x chains.
+//
+// Replaces the sampling half of Worker.tilted (reference epstan/method.py:338-408,
+// _sample_stan :43-118, util.stan_sample_time util.py:692-724), i.e. one PyStan
+// 2.17 `StanModel.sampling` call per site per EP iteration, by ONE persistent
+// kernel launch: one CTA per site, all chains of the site advanced in lock-step
+// at the granularity of a gradient evaluation ("tick").
+//
+//   tick = [per-chain warps]  consume the previous gradient, run the NUTS state
+//                             machine until the chain needs the next gradient
+//          [whole CTA]        likelihood pass for all chains at once:
+//                               F = X B'      (rows x chains)      "forward"
+//                               E = y - sigmoid(F), lp += y F - softplus(F)
+//                               G = E' X      (chains x inputs)    "backward"
+//                             X_k is read ONCE per tick for both products; it
+//                             stays resident in shared memory when it fits,
+//                             otherwise it is streamed L2->smem with cp.async
+//                             double buffering.
+//
+// The densities are those of experiment/models/m{1,3,4}b[_sg].stan (see
+// oracle/density.py for the formulas); the sampler is Stan 2.17's adaptive
+// diag_e NUTS (multinomial trajectory sampling, generalised U-turn criterion,
+// dual-averaging step size, windowed variance adaptation) restated as an
+// iterative (stack based) tree builder so that it runs without recursion.
+// Arithmetic: fp32 for positions/momenta/gradients and the two contractions,
+// fp64 for the energies used in the accept/multinomial weights.
+#include "epg_internal.h"
+#include "epg_common.cuh"
+#include <math.h>
+#include <vector>
+
+#define NTHR 256
+#define NWARP (NTHR / 32)
+#define MAXDEPTH_CAP 12
+#define NCMAX 4
+
+// ---------------------------------------------------------------------------
+// site data
+// ---------------------------------------------------------------------------
+struct epg_site_data {
+    int model = 0, D = 0, S = 0;        // S: padded row stride (floats), column D holds 1.0
+    int K = 0;
+    int64_t N = 0;
+    float* X = nullptr;                 // [N][S]
+    float* y = nullptr;                 // [N]
+    int64_t* row0 = nullptr;            // [K+1]
+    int* grp_ptr = nullptr;             // [K+1] offsets into grp_rows
+    int* grp_rows = nullptr;            // per site: J+1 row offsets relative to the site start
+    std::vector<int64_t> h_row0;
+    std::vector<int> h_J, h_p;
+    int Pmax = 0, Jmax = 0;
+    int64_t max_rows = 0;
+    // sampler state
+    float* chain_mem = nullptr;         // [K*C][NVEC][P]
+    size_t chain_mem_bytes = 0;
+    float* last_q = nullptr;            // [K*C][P] last draw of every chain (init_prev)
+    size_t last_q_bytes = 0;
+    int last_C = 0;
+    float* omega = nullptr;             // [K][d*d] fp32 copy of the cavity precision
+    size_t omega_bytes = 0;
+    double* out = nullptr;              // per-site analytics
+    size_t out_bytes = 0;
+    double* ld_buf = nullptr;           // logdensity staging
+    size_t ld_bytes = 0;
+};
+
+void epg_sites_free(epg_ctx* c) {
+    epg_site_data* s = c->sites;
+    if (!s) return;
+    cudaFree(s->X); cudaFree(s->y); cudaFree(s->row0); cudaFree(s->grp_ptr); cudaFree(s->grp_rows);
+    cudaFree(s->chain_mem); cudaFree(s->last_q); cudaFree(s->omega); cudaFree(s->out); cudaFree(s->ld_buf);
+    delete s;
+    c->sites = nullptr;
+}
+
+namespace {
+
+__host__ __device__ inline int model_dphi(int model, int D) { return model == EPG_M4B ? 2 * D + 2 : D + 1; }
+__host__ __device__ inline int model_np(int model, int D, int J) {
+    return model_dphi(model, D) + J + (model == EPG_M1B ? 0 : J * D);
+}
+
+__global__ void k_convert_x(const double* __restrict__ src, float* __restrict__ dst, int64_t rows, int D, int S) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= rows * S) return;
+    const int64_t r = idx / S;
+    const int c = (int)(idx - r * S);
+    dst[idx] = c < D ? (float)src[r * D + c] : (c == D ? 1.0f : 0.0f);
+}
+__global__ void k_convert_y(const int64_t* __restrict__ src, float* __restrict__ dst, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[i] ? 1.0f : 0.0f;
+}
+
+// ---------------------------------------------------------------------------
+// RNG: Philox4x32-10, counter based.  key = (site seed, chain), counter =
+// (draw index, element, purpose).  Every lane of a warp can evaluate it
+// independently and get identical streams.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint4 philox4x32(uint4 ctr, uint2 key) {
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
+        ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+        key.x += 0x9E3779B9u;
+        key.y += 0xBB67AE85u;
+    }
+    return ctr;
+}
+__device__ __forceinline__ float u01(uint32_t x) { return ((float)(x >> 8) + 0.5f) * (1.0f / 16777216.0f); }
+__device__ __forceinline__ float rng_uniform(uint2 key, uint32_t& ctr) {
+    const uint4 r = philox4x32(make_uint4(ctr++, 0u, 1u, 0u), key);
+    return u01(r.x);
+}
+__device__ __forceinline__ float rng_normal(uint2 key, uint32_t ctr, uint32_t elem) {
+    const uint4 r = philox4x32(make_uint4(ctr, elem, 2u, 0u), key);
+    const float u1 = u01(r.x), u2 = u01(r.y);
+    return sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);
+}
+
+__device__ __forceinline__ double log_sum_exp(double a, double b) {
+    if (a == -INFINITY) return b;
+    if (b == -INFINITY) return a;
+    const double m = fmax(a, b);
+    return m + log1p(exp(-fabs(a - b)));
+}
+
+// per-chain vectors in global memory (stride P floats)
+enum {
+    V_Q = 0, V_P, V_G,            // working point z
+    V_QM, V_PM, V_GM,             // minus end of the trajectory
+    V_QP, V_PP, V_GP,             // plus end
+    V_RHO,                        // sum of momenta over the trajectory
+    V_QS, V_GS,                   // current sample
+    V_QPROP, V_GPROP,             // proposal of the node being built
+    V_CRHO, V_CPSL,               // node being built: rho and left-end p_sharp
+    V_MINV, V_WMEAN, V_WM2,       // inverse metric (diag), Welford accumulators
+    V_GL,                         // likelihood-gradient output of the batched pass
+    V_RS0, V_RQ0, V_RS1, V_RQ1,   // split-Rhat sums / sums of squares per half
+    V_STACK                       // + 4*level : psl, rho, qprop, gprop
+};
+#define NVEC (V_STACK + 4 * MAXDEPTH_CAP)
+
+enum { PH_START = 0, PH_START_WAIT, PH_SS_WAIT, PH_TREE_WAIT, PH_DONE, PH_DEAD };
+
+struct ChainS {
+    int phase, iter, depth, nleaf, sign, n_leap_tr, ss_dir, ss_first, init_tries, restart_ss;
+    uint32_t rng;
+    float eps;
+    double V, H0, Vs, lsw, sum_metro, cur_lsw, Vprop;
+    // dual averaging
+    double s_bar, x_bar, mu;
+    int da_count;
+    // variance windows
+    int win_count, win_next, win_size, w_n;
+    // analytics
+    double eps_sum;
+    long long n_leap_total;
+    int n_div;
+    double stack_lsw[MAXDEPTH_CAP], stack_V[MAXDEPTH_CAP];
+};
+
+struct SamplerArgs {
+    // site data
+    const float* X; const float* y; const int64_t* row0; const int* grp_ptr; const int* grp_rows;
+    int model, D, S, d;
+    // cavity
+    const double* cavQ; const double* cavm; float* omega;
+    // chains
+    float* chain_mem; float* last_q; int P, C;
+    int iter, warmup, init_mode, max_depth;
+    double delta;
+    int win_init, win_term, win_base;
+    const uint32_t* seeds;
+    // outputs
+    double* draws; int n_draws;     // [K][d][n]
+    double* out;                    // [K][4]: mean eps, max rhat, n_leapfrog, n_divergent
+    int k0;
+    // shared-memory plan
+    int R, resident, slices, NC, combos;
+    size_t off_E, off_B, off_G, off_gphi, off_lp, off_cs, smem_total;
+};
+
+__device__ __forceinline__ float* cvec(const SamplerArgs& a, int chain_global, int v) {
+    return a.chain_mem + ((size_t)chain_global * NVEC + v) * a.P;
+}
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+__device__ __forceinline__ float softplus_f(float f) { return fmaxf(f, 0.0f) + log1pf(__expf(-fabsf(f))); }
+__device__ __forceinline__ float sigmoid_f(float f) { return 1.0f / (1.0f + __expf(-f)); }
+
+// ---------------------------------------------------------------------------
+// Likelihood pass for all chains of one site: fills V_GL (likelihood part of
+// grad log p wrt every sampled parameter) and lp_out[c] (likelihood log-density).
+// ---------------------------------------------------------------------------
+template <int CP>
+__device__ void likelihood_pass(const SamplerArgs& a, unsigned char* smem, int site, int k_local, int nchains,
+                                int J, int64_t row_begin, int n_rows, const int* grows, double* lp_out) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int S = a.S, D = a.D, d = a.d, model = a.model;
+    float* Xs = reinterpret_cast<float*>(smem);
+    float* Et = reinterpret_cast<float*>(smem + a.off_E);
+    float* Bm = reinterpret_cast<float*>(smem + a.off_B);
+    float* Gp = reinterpret_cast<float*>(smem + a.off_G);
+    float* gphi = reinterpret_cast<float*>(smem + a.off_gphi);
+    double* lpw = reinterpret_cast<double*>(smem + a.off_lp);      // [NWARP][CP]
+    const int R = a.R;
+    const int S4 = S >> 2;
+    const int chain0 = k_local * a.C;
+    const int ia = (model == EPG_M4B) ? 1 : 0;                      // index of log sigma_a in phi
+    const int ib = (model == EPG_M4B) ? 2 + D : 1;                  // start of log sigma_b (m3b/m4b)
+
+    for (int e = tid; e < CP * d; e += NTHR) gphi[e] = 0.0f;
+    float lpacc[CP];
+#pragma unroll
+    for (int c = 0; c < CP; ++c) lpacc[c] = 0.0f;
+
+    // B2 work assignment
+    const int combos = a.combos, slices = a.slices, NC = a.NC;
+    const int my_slice = (NC == 1) ? tid / combos : 0;
+    const bool b2_active = (NC > 1) || (my_slice < slices);
+    const int combo0 = (NC == 1) ? tid % combos : tid;
+
+    int tile_parity = 0;
+    for (int j = 0; j < J; ++j) {
+        const int g_begin = grows[j], g_end = grows[j + 1];
+        // ---- coefficients of group j: Bm[c][0..D) = beta_j(c), Bm[c][D] = alpha_j(c) ----
+        __syncthreads();
+        for (int e = tid; e < CP * S; e += NTHR) {
+            const int c = e / S, col = e - c * S;
+            float v = 0.0f;
+            if (c < nchains && col <= D) {
+                const float* q = cvec(a, chain0 + c, V_Q);
+                if (col == D) {
+                    const float sa = __expf(q[ia]);
+                    v = q[d + j] * sa + (model == EPG_M4B ? q[0] : 0.0f);
+                } else if (model == EPG_M1B) {
+                    v = q[1 + col];
+                } else {
+                    const float etb = q[d + J + j * D + col];
+                    v = etb * __expf(q[ib + col]) + (model == EPG_M4B ? q[2 + col] : 0.0f);
+                }
+            }
+            Bm[e] = v;
+        }
+        float acc[NCMAX][16];
+#pragma unroll
+        for (int u = 0; u < NCMAX; ++u)
+#pragma unroll
+            for (int q = 0; q < 16; ++q) acc[u][q] = 0.0f;
+
+        const int n_tiles = (g_end - g_begin + R - 1) / R;
+        // streaming: prefetch the first tile of the group
+        if (!a.resident && n_tiles > 0) {
+            const int rows = min(R, g_end - g_begin);
+            const float4* src = reinterpret_cast<const float4*>(a.X + (size_t)(row_begin + g_begin) * S);
+            float4* dst = reinterpret_cast<float4*>(Xs + (size_t)tile_parity * R * S);
+            for (int e = tid; e < rows * S4; e += NTHR) cp_async16(dst + e, src + e);
+            cp_async_commit();
+        }
+        for (int t = 0; t < n_tiles; ++t) {
+            const int r0 = g_begin + t * R;
+            const int rows = min(R, g_end - r0);
+            const float* Xt;
+            if (a.resident) {
+                Xt = Xs + (size_t)r0 * S;
+                __syncthreads();                       // Bm ready / previous tile's Et consumed
+            } else {
+                cp_async_wait<0>();
+                __syncthreads();                       // tile t landed; everyone left tile t-1
+                if (t + 1 < n_tiles) {
+                    const int rows_n = min(R, g_end - (r0 + R));
+                    const float4* src = reinterpret_cast<const float4*>(a.X + (size_t)(row_begin + r0 + R) * S);
+                    float4* dst = reinterpret_cast<float4*>(Xs + (size_t)(tile_parity ^ 1) * R * S);
+                    for (int e = tid; e < rows_n * S4; e += NTHR) cp_async16(dst + e, src + e);
+                    cp_async_commit();
+                }
+                Xt = Xs + (size_t)tile_parity * R * S;
+                tile_parity ^= 1;
+            }
+            // ---- B1: F = X B', E = y - sigmoid(F), lp ----
+            if (tid < rows) {
+                float f[CP];
+#pragma unroll
+                for (int c = 0; c < CP; ++c) f[c] = 0.0f;
+                const float4* xr = reinterpret_cast<const float4*>(Xt + (size_t)tid * S);
+                for (int i = 0; i < S4; ++i) {
+                    const float4 x = xr[i];
+#pragma unroll
+                    for (int c = 0; c < CP; ++c) {
+                        const float4 b = reinterpret_cast<const float4*>(Bm + c * S)[i];
+                        f[c] = fmaf(x.x, b.x, fmaf(x.y, b.y, fmaf(x.z, b.z, fmaf(x.w, b.w, f[c]))));
+                    }
+                }
+                const float yv = a.y[row_begin + r0 + tid];
+#pragma unroll
+                for (int c = 0; c < CP; ++c) {
+                    lpacc[c] += yv * f[c] - softplus_f(f[c]);
+                    f[c] = yv - sigmoid_f(f[c]);
+                }
+#pragma unroll
+                for (int c4 = 0; c4 < CP / 4; ++c4)
+                    reinterpret_cast<float4*>(Et + (size_t)tid * CP)[c4] =
+                        make_float4(f[4 * c4], f[4 * c4 + 1], f[4 * c4 + 2], f[4 * c4 + 3]);
+            }
+            __syncthreads();
+            // ---- B2: G += E' X  (4 inputs x 4 chains register tiles) ----
+            if (b2_active) {
+#pragma unroll
+                for (int u = 0; u < NCMAX; ++u) {
+                    const int combo = combo0 + u * NTHR;
+                    if (u < NC && combo < combos) {
+                        const int dq = combo % S4, cg = combo / S4;
+                        for (int r = my_slice; r < rows; r += slices) {
+                            const float4 x = reinterpret_cast<const float4*>(Xt + (size_t)r * S)[dq];
+                            const float4 e = reinterpret_cast<const float4*>(Et + (size_t)r * CP)[cg];
+                            acc[u][0] = fmaf(x.x, e.x, acc[u][0]);   acc[u][1] = fmaf(x.x, e.y, acc[u][1]);
+                            acc[u][2] = fmaf(x.x, e.z, acc[u][2]);   acc[u][3] = fmaf(x.x, e.w, acc[u][3]);
+                            acc[u][4] = fmaf(x.y, e.x, acc[u][4]);   acc[u][5] = fmaf(x.y, e.y, acc[u][5]);
+                            acc[u][6] = fmaf(x.y, e.z, acc[u][6]);   acc[u][7] = fmaf(x.y, e.w, acc[u][7]);
+                            acc[u][8] = fmaf(x.z, e.x, acc[u][8]);   acc[u][9] = fmaf(x.z, e.y, acc[u][9]);
+                            acc[u][10] = fmaf(x.z, e.z, acc[u][10]); acc[u][11] = fmaf(x.z, e.w, acc[u][11]);
+                            acc[u][12] = fmaf(x.w, e.x, acc[u][12]); acc[u][13] = fmaf(x.w, e.y, acc[u][13]);
+                            acc[u][14] = fmaf(x.w, e.z, acc[u][14]); acc[u][15] = fmaf(x.w, e.w, acc[u][15]);
+                        }
+                    }
+                }
+            }
+        }
+        // ---- group end: G_part[slice][c][col] ----
+        __syncthreads();
+        if (b2_active) {
+#pragma unroll
+            for (int u = 0; u < NCMAX; ++u) {
+                const int combo = combo0 + u * NTHR;
+                if (u < NC && combo < combos) {
+                    const int dq = combo % S4, cg = combo / S4;
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) {
+                        const int col = 4 * dq + (q >> 2), c = 4 * cg + (q & 3);
+                        Gp[((size_t)my_slice * CP + c) * S + col] = acc[u][q];
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        // ---- fixed-order slice reduction + chain rule of group j ----
+        for (int e = tid; e < CP * S; e += NTHR) {
+            const int c = e / S, col = e - c * S;
+            if (c >= nchains || col > D) continue;
+            float gsum = 0.0f;
+            for (int sl = 0; sl < slices; ++sl) gsum += Gp[((size_t)sl * CP + c) * S + col];
+            const float* q = cvec(a, chain0 + c, V_Q);
+            float* gl = cvec(a, chain0 + c, V_GL);
+            if (col == D) {
+                // s_j = sum_n e_n
+                const float sa = __expf(q[ia]);
+                const float eta = q[d + j];
+                gl[d + j] = sa * gsum;
+                gphi[c * d + ia] += sa * eta * gsum;      // (c, col) pairs own distinct slots
+                if (model == EPG_M4B) gphi[c * d + 0] += gsum;
+            } else if (model == EPG_M1B) {
+                gphi[c * d + 1 + col] += gsum;
+            } else {
+                const float sb = __expf(q[ib + col]);
+                const float etb = q[d + J + j * D + col];
+                gl[d + J + j * D + col] = sb * gsum;
+                gphi[c * d + ib + col] += sb * etb * gsum;
+                if (model == EPG_M4B) gphi[c * d + 2 + col] += gsum;
+            }
+        }
+    }
+    // ---- lp reduction (fp64) and phi gradient write-back ----
+#pragma unroll
+    for (int c = 0; c < CP; ++c) {
+        const double v = warp_sum((double)lpacc[c]);
+        if (lane == 0) lpw[warp * CP + c] = v;
+    }
+    __syncthreads();
+    if (tid < nchains) {
+        double s = 0.0;
+        for (int w = 0; w < NWARP; ++w) s += lpw[w * CP + tid];
+        lp_out[tid] = s;
+    }
+    for (int e = tid; e < CP * d; e += NTHR) {
+        const int c = e / d, i = e - c * d;
+        if (c < nchains) cvec(a, chain0 + c, V_GL)[i] = gphi[e];
+    }
+    __syncthreads();
+}
+
+// ---------------------------------------------------------------------------
+// per-chain (one warp) helpers
+// ---------------------------------------------------------------------------
+struct ChainCtx {
+    const SamplerArgs& a;
+    int cg;          // global chain index (k_local*C + c)
+    int p, d, J, D, lane;
+    uint2 key;
+    const float* omega;   // [d*d] fp32 cavity precision
+    const double* mu;     // [d]
+    __device__ float* v(int which) const { return cvec(a, cg, which); }
+};
+
+__device__ __forceinline__ void vcopy(const ChainCtx& x, int dst, int src) {
+    float* D_ = x.v(dst); const float* S_ = x.v(src);
+    for (int i = x.lane; i < x.p; i += 32) D_[i] = S_[i];
+}
+
+// kinetic energy 0.5 p' M^-1 p
+__device__ __forceinline__ double kinetic(const ChainCtx& x, const float* p) {
+    const float* minv = x.v(V_MINV);
+    float s = 0.0f;
+    for (int i = x.lane; i < x.p; i += 32) s += minv[i] * p[i] * p[i];
+    return 0.5 * warp_sum((double)s);
+}
+
+// full gradient / potential from the likelihood pass output:
+//   V = -(lp_lik + lp_prior),  g = dV/dq
+__device__ double finish_gradient(const ChainCtx& x, double lp_lik) {
+    const float* q = x.v(V_Q);
+    const float* gl = x.v(V_GL);
+    float* g = x.v(V_G);
+    const int d = x.d;
+    float quad = 0.0f, sq = 0.0f;
+    for (int i = x.lane; i < d; i += 32) {
+        float ci = 0.0f;
+        for (int j = 0; j < d; ++j) ci = fmaf(x.omega[i + (size_t)j * d], q[j] - (float)x.mu[j], ci);
+        quad += ci * (q[i] - (float)x.mu[i]);
+        g[i] = ci - gl[i];
+    }
+    for (int i = d + x.lane; i < x.p; i += 32) {
+        const float qi = q[i];
+        sq += qi * qi;
+        g[i] = qi - gl[i];
+    }
+    const double prior = -0.5 * warp_sum((double)quad) - 0.5 * warp_sum((double)sq);
+    __syncwarp();
+    return -(lp_lik + prior);
+}
+
+__device__ void sample_momentum(const ChainCtx& x, ChainS& s) {
+    const float* minv = x.v(V_MINV);
+    float* p = x.v(V_P);
+    const uint32_t ctr = s.rng++;
+    for (int i = x.lane; i < x.p; i += 32) p[i] = rng_normal(x.key, ctr, (uint32_t)i) * rsqrtf(minv[i]);
+    __syncwarp();
+}
+
+// first half of a leapfrog step from the working point: p -= e/2 g ; q += e M^-1 p
+__device__ void leapfrog_begin(const ChainCtx& x, float eps_signed) {
+    float* q = x.v(V_Q); float* p = x.v(V_P); const float* g = x.v(V_G); const float* minv = x.v(V_MINV);
+    for (int i = x.lane; i < x.p; i += 32) {
+        const float ph = p[i] - 0.5f * eps_signed * g[i];
+        p[i] = ph;
+        q[i] += eps_signed * minv[i] * ph;
+    }
+    __syncwarp();
+}
+__device__ void leapfrog_end(const ChainCtx& x, float eps_signed) {
+    float* p = x.v(V_P); const float* g = x.v(V_G);
+    for (int i = x.lane; i < x.p; i += 32) p[i] -= 0.5f * eps_signed * g[i];
+    __syncwarp();
+}
+
+__device__ void begin_ss_trial(const ChainCtx& x, ChainS& s) {
+    vcopy(x, V_Q, V_QS);
+    vcopy(x, V_G, V_GS);
+    __syncwarp();
+    sample_momentum(x, s);
+    s.H0 = s.Vs + kinetic(x, x.v(V_P));
+    leapfrog_begin(x, s.eps);
+    s.phase = PH_SS_WAIT;
+}
+
+__device__ void issue_leapfrog(const ChainCtx& x, ChainS& s) {
+    leapfrog_begin(x, s.sign * s.eps);
+    s.phase = PH_TREE_WAIT;
+}
+
+__device__ void begin_subtree(const ChainCtx& x, ChainS& s) {
+    const float u = rng_uniform(x.key, s.rng);
+    s.sign = (u > 0.5f) ? 1 : -1;
+    if (s.sign > 0) { vcopy(x, V_Q, V_QP); vcopy(x, V_P, V_PP); vcopy(x, V_G, V_GP); }
+    else            { vcopy(x, V_Q, V_QM); vcopy(x, V_P, V_PM); vcopy(x, V_G, V_GM); }
+    __syncwarp();
+    s.nleaf = 0;
+    issue_leapfrog(x, s);
+}
+
+__device__ void begin_transition(const ChainCtx& x, ChainS& s) {
+    vcopy(x, V_Q, V_QS);
+    vcopy(x, V_G, V_GS);
+    __syncwarp();
+    sample_momentum(x, s);
+    s.V = s.Vs;
+    s.H0 = s.Vs + kinetic(x, x.v(V_P));
+    vcopy(x, V_QM, V_Q); vcopy(x, V_PM, V_P); vcopy(x, V_GM, V_G);
+    vcopy(x, V_QP, V_Q); vcopy(x, V_PP, V_P); vcopy(x, V_GP, V_G);
+    vcopy(x, V_RHO, V_P);
+    __syncwarp();
+    s.lsw = 0.0;
+    s.depth = 0;
+    s.n_leap_tr = 0;
+    s.sum_metro = 0.0;
+    begin_subtree(x, s);
+}
+
+// Stan 2.17 windowed_adaptation::compute_next_window
+__device__ void next_window(const SamplerArgs& a, ChainS& s) {
+    const int last = a.warmup - a.win_term - 1;
+    if (s.win_next == last) return;
+    s.win_size *= 2;
+    s.win_next = s.win_count + s.win_size;
+    if (s.win_next == last) return;
+    const int boundary = s.win_next + 2 * s.win_size;
+    if (boundary >= a.warmup - a.win_term) s.win_next = last;
+}
+
+// bookkeeping at the end of a transition; returns with the next request issued
+// (or the chain finished)
+__device__ void end_transition(const ChainCtx& x, ChainS& s, int c_local, int k_global_draw_site) {
+    const SamplerArgs& a = x.a;
+    const double accept = s.n_leap_tr > 0 ? s.sum_metro / (double)s.n_leap_tr : 0.0;
+    s.n_leap_total += s.n_leap_tr;
+    const float* qs = x.v(V_QS);
+    bool restart_ss = false;
+    if (s.iter < a.warmup) {
+        // ---- dual averaging (stepsize_adaptation::learn_stepsize) ----
+        s.da_count += 1;
+        const double stat = accept > 1.0 ? 1.0 : accept;
+        const double eta = 1.0 / (s.da_count + 10.0);
+        s.s_bar = (1.0 - eta) * s.s_bar + eta * (a.delta - stat);
+        const double xx = s.mu - s.s_bar * sqrt((double)s.da_count) / 0.05;
+        const double x_eta = pow((double)s.da_count, -0.75);
+        s.x_bar = (1.0 - x_eta) * s.x_bar + x_eta * xx;
+        s.eps = (float)exp(xx);
+        // ---- variance windows (var_adaptation::learn_variance) ----
+        const bool in_win = a.warmup >= 20 && s.win_count >= a.win_init &&
+                            s.win_count < a.warmup - a.win_term && s.win_count != a.warmup;
+        if (in_win) {
+            s.w_n += 1;
+            float* wm = x.v(V_WMEAN); float* w2 = x.v(V_WM2);
+            for (int i = x.lane; i < x.p; i += 32) {
+                const float dlt = qs[i] - wm[i];
+                wm[i] += dlt / (float)s.w_n;
+                w2[i] += (qs[i] - wm[i]) * dlt;
+            }
+        }
+        const bool win_end = a.warmup >= 20 && s.win_count == s.win_next && s.win_count != a.warmup;
+        if (win_end) {
+            next_window(a, s);
+            const float n = (float)s.w_n;
+            float* minv = x.v(V_MINV); float* wm = x.v(V_WMEAN); float* w2 = x.v(V_WM2);
+            for (int i = x.lane; i < x.p; i += 32) {
+                const float var = w2[i] / (n - 1.0f);
+                minv[i] = (n / (n + 5.0f)) * var + 1e-3f * (5.0f / (n + 5.0f));
+                wm[i] = 0.0f; w2[i] = 0.0f;
+            }
+            s.w_n = 0;
+            restart_ss = true;
+        }
+        s.win_count += 1;
+    } else {
+        // ---- store the draw of phi and accumulate split-Rhat sums ----
+        const int t = s.iter - a.warmup;
+        const int per = a.iter - a.warmup;
+        double* dst = a.draws + (size_t)k_global_draw_site * a.d * a.n_draws;
+        for (int i = x.lane; i < a.d; i += 32) dst[(size_t)i * a.n_draws + c_local * per + t] = (double)qs[i];
+        const int half = (t < per / 2) ? 0 : 1;
+        if (t < 2 * (per / 2)) {
+            float* rs = x.v(half ? V_RS1 : V_RS0); float* rq = x.v(half ? V_RQ1 : V_RQ0);
+            // centred on the first draw for accuracy: stored in WMEAN after warm-up
+            const float* ref = x.v(V_WMEAN);
+            for (int i = x.lane; i < x.p; i += 32) {
+                const float dv = qs[i] - ref[i];
+                rs[i] += dv; rq[i] += dv * dv;
+            }
+        }
+        s.eps_sum += s.eps;
+    }
+    __syncwarp();
+    s.iter += 1;
+    if (s.iter == a.warmup && a.warmup > 0) {
+        s.eps = (float)exp(s.x_bar);                 // complete_adaptation
+        restart_ss = false;
+    }
+    if (s.iter == a.warmup) {
+        // reference point for the Rhat sums
+        float* ref = x.v(V_WMEAN);
+        for (int i = x.lane; i < x.p; i += 32) ref[i] = qs[i];
+        __syncwarp();
+    }
+    if (s.iter >= a.iter) {
+        float* lq = a.last_q + (size_t)x.cg * a.P;
+        for (int i = x.lane; i < x.p; i += 32) lq[i] = qs[i];
+        s.phase = PH_DONE;
+        return;
+    }
+    if (restart_ss) {
+        s.ss_first = 1;
+        s.restart_ss = 1;
+        begin_ss_trial(x, s);
+    } else {
+        begin_transition(x, s);
+    }
+}
+
+// One step of the per-chain state machine: consume the gradient that was just
+// evaluated at V_Q (lp_lik) and advance until the next evaluation is requested.
+__device__ void chain_step(const ChainCtx& x, ChainS& s, double lp_lik, int c_local, int site_draw) {
+    const SamplerArgs& a = x.a;
+    if (s.phase == PH_DONE || s.phase == PH_DEAD) return;
+    if (s.phase == PH_START_WAIT) {
+        const double V0 = finish_gradient(x, lp_lik);
+        bool fin = isfinite(V0);
+        const float* g = x.v(V_G);
+        float bad = 0.0f;
+        for (int i = x.lane; i < x.p; i += 32) if (!isfinite(g[i])) bad = 1.0f;
+        fin = fin && (warp_sum(bad) == 0.0f);
+        if (fin) {
+            s.Vs = V0;
+            vcopy(x, V_QS, V_Q);
+            vcopy(x, V_GS, V_G);
+            __syncwarp();
+            s.ss_first = 1;
+            s.restart_ss = 0;
+            begin_ss_trial(x, s);
+            return;
+        }
+        if (a.init_mode == 0 && s.init_tries < 100) { s.init_tries++; s.phase = PH_START; }   // redraw below
+        else { s.phase = PH_DEAD; return; }
+    }
+    if (s.phase == PH_START) {
+        float* q = x.v(V_Q);
+        if (a.init_mode == 2) {
+            const float* lq = a.last_q + (size_t)x.cg * a.P;
+            for (int i = x.lane; i < x.p; i += 32) q[i] = lq[i];
+        } else if (a.init_mode == 1) {
+            for (int i = x.lane; i < x.p; i += 32) q[i] = 0.0f;
+        } else {
+            const uint32_t ctr = s.rng++;
+            for (int i = x.lane; i < x.p; i += 32) {
+                const uint4 r = philox4x32(make_uint4(ctr, (uint32_t)i, 3u, 0u), x.key);
+                q[i] = 4.0f * u01(r.x) - 2.0f;       // Stan's default init: U(-2, 2)
+            }
+        }
+        __syncwarp();
+        s.phase = PH_START_WAIT;
+        return;
+    }
+    // ---- consume ----
+    const double Vnew = finish_gradient(x, lp_lik);
+    if (s.phase == PH_SS_WAIT) {
+        leapfrog_end(x, s.eps);
+        double h = Vnew + kinetic(x, x.v(V_P));
+        if (isnan(h)) h = INFINITY;
+        const double dH = s.H0 - h;
+        const double thr = log(0.8);
+        s.n_leap_total += 1;
+        if (s.ss_first) {
+            s.ss_dir = (dH > thr) ? 1 : -1;
+            s.ss_first = 0;
+            begin_ss_trial(x, s);
+            return;
+        }
+        const bool stop = (s.ss_dir == 1) ? !(dH > thr) : !(dH < thr);
+        if (stop || s.eps > 1e7f || s.eps < 1e-30f) {
+            if (s.restart_ss) {            // after a metric update: restart dual averaging
+                s.mu = log(10.0 * (double)s.eps);
+                s.s_bar = 0.0; s.x_bar = 0.0; s.da_count = 0;
+                s.restart_ss = 0;
+            }
+            begin_transition(x, s);
+            return;
+        }
+        s.eps = (s.ss_dir == 1) ? 2.0f * s.eps : 0.5f * s.eps;
+        begin_ss_trial(x, s);
+        return;
+    }
+    // ---- PH_TREE_WAIT: a new leaf of the current subtree ----
+    const float es = s.sign * s.eps;
+    leapfrog_end(x, es);
+    s.V = Vnew;
+    double h = Vnew + kinetic(x, x.v(V_P));
+    if (isnan(h)) h = INFINITY;
+    s.n_leap_tr += 1;
+    const double dH = s.H0 - h;
+    s.sum_metro += (dH > 0.0) ? 1.0 : exp(dH);
+    if (-dH > 1000.0) {                 // divergent: the subtree is discarded
+        s.n_div += 1;
+        end_transition(x, s, c_local, site_draw);
+        return;
+    }
+    // leaf node: rho = p, p_sharp(left) = M^-1 p, proposal = this point
+    {
+        const float* p = x.v(V_P); const float* minv = x.v(V_MINV);
+        float* crho = x.v(V_CRHO); float* cpsl = x.v(V_CPSL);
+        const float* q = x.v(V_Q); const float* g = x.v(V_G);
+        float* qp_ = x.v(V_QPROP); float* gp_ = x.v(V_GPROP);
+        for (int i = x.lane; i < x.p; i += 32) {
+            crho[i] = p[i]; cpsl[i] = minv[i] * p[i];
+            qp_[i] = q[i]; gp_[i] = g[i];
+        }
+        __syncwarp();
+    }
+    s.cur_lsw = dH;
+    s.Vprop = Vnew;
+    int l = 0;
+    while ((s.nleaf >> l) & 1) {
+        // merge the pending left sibling at level l with the node just completed
+        const int base = V_STACK + 4 * l;
+        const double lsw_sub = log_sum_exp(s.stack_lsw[l], s.cur_lsw);
+        bool take_right = s.cur_lsw > lsw_sub;
+        if (!take_right) take_right = rng_uniform(x.key, s.rng) < (float)exp(s.cur_lsw - lsw_sub);
+        const float* lpsl = x.v(base + 0); const float* lrho = x.v(base + 1);
+        float* crho = x.v(V_CRHO); float* cpsl = x.v(V_CPSL);
+        const float* p = x.v(V_P); const float* minv = x.v(V_MINV);
+        float d1 = 0.0f, d2 = 0.0f;
+        for (int i = x.lane; i < x.p; i += 32) {
+            const float rs = lrho[i] + crho[i];
+            crho[i] = rs;
+            const float pl = lpsl[i];
+            cpsl[i] = pl;
+            d1 += pl * rs;
+            d2 += minv[i] * p[i] * rs;
+        }
+        d1 = warp_sum(d1); d2 = warp_sum(d2);
+        if (!take_right) {
+            vcopy(x, V_QPROP, base + 2);
+            vcopy(x, V_GPROP, base + 3);
+            s.Vprop = s.stack_V[l];
+        }
+        __syncwarp();
+        s.cur_lsw = lsw_sub;
+        if (!(d1 > 0.0f && d2 > 0.0f)) {        // U-turn inside the new subtree: discard it
+            end_transition(x, s, c_local, site_draw);
+            return;
+        }
+        ++l;
+    }
+    if (l < s.depth) {
+        const int base = V_STACK + 4 * l;
+        vcopy(x, base + 0, V_CPSL); vcopy(x, base + 1, V_CRHO);
+        vcopy(x, base + 2, V_QPROP); vcopy(x, base + 3, V_GPROP);
+        s.stack_lsw[l] = s.cur_lsw;
+        s.stack_V[l] = s.Vprop;
+        __syncwarp();
+        s.nleaf += 1;
+        issue_leapfrog(x, s);
+        return;
+    }
+    // ---- the subtree of 2^depth leaves is complete and valid ----
+    if (s.sign > 0) { vcopy(x, V_QP, V_Q); vcopy(x, V_PP, V_P); vcopy(x, V_GP, V_G); }
+    else            { vcopy(x, V_QM, V_Q); vcopy(x, V_PM, V_P); vcopy(x, V_GM, V_G); }
+    s.depth += 1;
+    bool take = s.cur_lsw > s.lsw;
+    if (!take) take = rng_uniform(x.key, s.rng) < (float)exp(s.cur_lsw - s.lsw);
+    if (take) { vcopy(x, V_QS, V_QPROP); vcopy(x, V_GS, V_GPROP); s.Vs = s.Vprop; }
+    s.lsw = log_sum_exp(s.lsw, s.cur_lsw);
+    __syncwarp();
+    float d1 = 0.0f, d2 = 0.0f;
+    {
+        float* rho = x.v(V_RHO); const float* crho = x.v(V_CRHO);
+        const float* pm = x.v(V_PM); const float* pp = x.v(V_PP); const float* minv = x.v(V_MINV);
+        for (int i = x.lane; i < x.p; i += 32) {
+            const float r = rho[i] + crho[i];
+            rho[i] = r;
+            d1 += minv[i] * pm[i] * r;
+            d2 += minv[i] * pp[i] * r;
+        }
+        d1 = warp_sum(d1); d2 = warp_sum(d2);
+        __syncwarp();
+    }
+    if (!(d1 > 0.0f && d2 > 0.0f) || s.depth >= a.max_depth) {
+        end_transition(x, s, c_local, site_draw);
+        return;
+    }
+    begin_subtree(x, s);
+}
+
+// ---------------------------------------------------------------------------
+// the persistent sampling kernel: one CTA per site
+// ---------------------------------------------------------------------------
+template <int CP>
+__global__ void __launch_bounds__(NTHR, 1) k_nuts(const SamplerArgs a) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int k_local = a.k0 + blockIdx.x;
+    const int C = a.C, d = a.d, D = a.D, S = a.S;
+    const int64_t row_begin = a.row0[k_local];
+    const int n_rows = (int)(a.row0[k_local + 1] - row_begin);
+    const int* grows = a.grp_rows + a.grp_ptr[k_local];
+    const int J = a.grp_ptr[k_local + 1] - a.grp_ptr[k_local] - 1;
+    const int p = model_np(a.model, D, J);
+    ChainS* cs = reinterpret_cast<ChainS*>(smem + a.off_cs);
+    __shared__ double lp_lik[32];
+    __shared__ int n_active;
+
+    // cavity precision -> fp32 copy (read by every chain every tick)
+    float* om = a.omega + (size_t)k_local * d * d;
+    const double* cq = a.cavQ + (size_t)k_local * d * d;
+    for (int e = tid; e < d * d; e += NTHR) om[e] = (float)cq[e];
+    // resident design matrix
+    if (a.resident) {
+        const float4* src = reinterpret_cast<const float4*>(a.X + (size_t)row_begin * S);
+        float4* dst = reinterpret_cast<float4*>(smem);
+        for (int e = tid; e < n_rows * (S >> 2); e += NTHR) dst[e] = src[e];
+    }
+    // chain state
+    for (int c = warp; c < C; c += NWARP) {
+        ChainS& s = cs[c];
+        const int cg = k_local * C + c;
+        if (lane == 0) {
+            memset(&s, 0, sizeof(ChainS));
+            s.phase = PH_START;
+            s.eps = 1.0f;
+            s.mu = log(10.0);
+            s.rng = 0;
+            s.win_next = a.win_init + a.win_base - 1;
+            s.win_size = a.win_base;
+        }
+        const int vecs[] = {V_WMEAN, V_WM2, V_RS0, V_RQ0, V_RS1, V_RQ1};
+        for (int i = lane; i < a.P; i += 32) {
+            cvec(a, cg, V_MINV)[i] = 1.0f;
+            for (int v = 0; v < 6; ++v) cvec(a, cg, vecs[v])[i] = 0.0f;
+        }
+    }
+    if (tid == 0) n_active = C;
+    __threadfence_block();
+    __syncthreads();
+
+    const uint32_t site_seed = a.seeds[blockIdx.x];
+    for (;;) {
+        // ---- per-chain state machines ----
+        for (int c = warp; c < C; c += NWARP) {
+            ChainCtx x{a, k_local * C + c, p, d, J, D, lane, make_uint2(site_seed, (uint32_t)c),
+                       om, a.cavm + (size_t)k_local * d};
+            ChainS s = cs[c];
+            const int before = s.phase;
+            chain_step(x, s, lp_lik[c], c, k_local);
+            __syncwarp();
+            if (lane == 0) {
+                cs[c] = s;
+                if ((s.phase == PH_DONE || s.phase == PH_DEAD) && !(before == PH_DONE || before == PH_DEAD))
+                    atomicSub(&n_active, 1);
+            }
+        }
+        __threadfence_block();
+        __syncthreads();
+        if (n_active <= 0) break;
+        likelihood_pass<CP>(a, smem, k_local, k_local, C, J, row_begin, n_rows, grows, lp_lik);
+    }
+
+    // ---- per-site analytics: mean step size, max split-Rhat, leapfrogs ----
+    __syncthreads();
+    if (warp == 0) {
+        const int per = a.iter - a.warmup;
+        const int hn = per / 2;
+        float worst = 0.0f;
+        if (hn >= 2 && C >= 1) {
+            for (int i = lane; i < p; i += 32) {
+                // split chains: 2C sequences of hn draws
+                float mean_all = 0.0f, W = 0.0f;
+                int m = 0;
+                for (int c = 0; c < C; ++c) {
+                    if (cs[c].phase != PH_DONE) continue;
+                    const int cg = k_local * C + c;
+                    for (int h = 0; h < 2; ++h) {
+                        const float sm = cvec(a, cg, h ? V_RS1 : V_RS0)[i];
+                        const float sq = cvec(a, cg, h ? V_RQ1 : V_RQ0)[i];
+                        const float ref = cvec(a, cg, V_WMEAN)[i];
+                        const float mu = sm / hn;
+                        W += (sq - hn * mu * mu) / (hn - 1);
+                        mean_all += mu + ref;
+                        ++m;
+                    }
+                }
+                if (m >= 2) {
+                    mean_all /= m; W /= m;
+                    float B = 0.0f;
+                    for (int c = 0; c < C; ++c) {
+                        if (cs[c].phase != PH_DONE) continue;
+                        const int cg = k_local * C + c;
+                        for (int h = 0; h < 2; ++h) {
+                            const float mu = cvec(a, cg, h ? V_RS1 : V_RS0)[i] / hn + cvec(a, cg, V_WMEAN)[i];
+                            B += (mu - mean_all) * (mu - mean_all);
+                        }
+                    }
+                    B = B * hn / (m - 1);
+                    const float var_plus = (hn - 1.0f) / hn * W + B / hn;
+                    const float rhat = W > 0.0f ? sqrtf(var_plus / W) : 1.0f;
+                    worst = fmaxf(worst, rhat);
+                }
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) worst = fmaxf(worst, __shfl_xor_sync(0xffffffffu, worst, o));
+        if (lane == 0) {
+            double eps_mean = 0.0, nl = 0.0, nd = 0.0;
+            int ok = 0;
+            for (int c = 0; c < C; ++c) {
+                nl += (double)cs[c].n_leap_total;
+                nd += cs[c].n_div;
+                if (cs[c].phase == PH_DONE) { eps_mean += cs[c].eps_sum / (per > 0 ? per : 1); ++ok; }
+            }
+            double* o = a.out + (size_t)k_local * 4;
+            o[0] = ok ? eps_mean / ok : NAN;
+            o[1] = (ok == C) ? (double)worst : NAN;
+            o[2] = nl;
+            o[3] = (ok == C) ? nd : -1.0;
+        }
+    }
+}
+
+// log-density / gradient at caller-supplied points (parity tests)
+template <int CP>
+__global__ void __launch_bounds__(NTHR, 1) k_logdensity(const SamplerArgs a, int nq, double* lp_out, double* grad_out) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int k_local = a.k0;
+    const int d = a.d, D = a.D, S = a.S;
+    const int64_t row_begin = a.row0[k_local];
+    const int n_rows = (int)(a.row0[k_local + 1] - row_begin);
+    const int* grows = a.grp_rows + a.grp_ptr[k_local];
+    const int J = a.grp_ptr[k_local + 1] - a.grp_ptr[k_local] - 1;
+    const int p = model_np(a.model, D, J);
+    __shared__ double lp_lik[32];
+    float* om = a.omega + (size_t)k_local * d * d;
+    const double* cq = a.cavQ + (size_t)k_local * d * d;
+    for (int e = tid; e < d * d; e += NTHR) om[e] = (float)cq[e];
+    if (a.resident) {
+        const float4* src = reinterpret_cast<const float4*>(a.X + (size_t)row_begin * S);
+        float4* dst = reinterpret_cast<float4*>(smem);
+        for (int e = tid; e < n_rows * (S >> 2); e += NTHR) dst[e] = src[e];
+    }
+    __threadfence_block();
+    __syncthreads();
+    likelihood_pass<CP>(a, smem, k_local, k_local, nq, J, row_begin, n_rows, grows, lp_lik);
+    for (int c = warp; c < nq; c += NWARP) {
+        ChainCtx x{a, k_local * a.C + c, p, d, J, D, lane, make_uint2(0u, 0u), om, a.cavm + (size_t)k_local * d};
+        const double V = finish_gradient(x, lp_lik[c]);
+        const float* g = x.v(V_G);
+        if (lane == 0) lp_out[c] = -V;
+        for (int i = lane; i < p; i += 32) grad_out[(size_t)c * p + i] = -(double)g[i];
+    }
+}
+
+__global__ void k_set_q(float* chain_mem, int chain0, int P, int p, int nq, const double* q) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= nq * p) return;
+    const int c = idx / p, i = idx - c * p;
+    chain_mem[((size_t)(chain0 + c) * NVEC + V_Q) * P + i] = (float)q[idx];
+}
+
+// shared-memory plan for a launch
+bool plan_smem(SamplerArgs& a, int CP, int64_t max_rows, int d) {
+    const size_t budget = 227 * 1024 - 1024;
+    const int S = a.S;
+    const int S4 = S / 4;
+    a.combos = S4 * (CP / 4);
+    if (a.combos <= NTHR) { a.NC = 1; a.slices = NTHR / a.combos; if (a.slices > 16) a.slices = 16; }
+    else { a.NC = (a.combos + NTHR - 1) / NTHR; a.slices = 1; if (a.NC > NCMAX) return false; }
+    a.R = NTHR;
+    for (;;) {
+        size_t fixed = 0;
+        fixed += sizeof(float) * (size_t)a.R * CP;                       // E
+        fixed = (fixed + 15) & ~(size_t)15;
+        const size_t szB = sizeof(float) * (size_t)CP * S;
+        const size_t szG = sizeof(float) * (size_t)a.slices * CP * S;
+        const size_t szg = sizeof(float) * (size_t)CP * d;
+        const size_t szl = sizeof(double) * (size_t)NWARP * CP;
+        const size_t szc = sizeof(ChainS) * 32;
+        size_t rest = fixed + szB + szG + ((szg + 15) & ~(size_t)15) + szl + szc + 64;
+        const size_t xres = sizeof(float) * (size_t)max_rows * S;
+        size_t xbytes;
+        if (xres + rest <= budget) { a.resident = 1; xbytes = xres; }
+        else { a.resident = 0; xbytes = 2 * sizeof(float) * (size_t)a.R * S; }
+        xbytes = (xbytes + 15) & ~(size_t)15;
+        if (xbytes + rest <= budget) {
+            size_t o = xbytes;
+            a.off_E = o; o += fixed;
+            a.off_B = o; o += szB;
+            a.off_G = o; o += szG;
+            a.off_gphi = o; o += (szg + 15) & ~(size_t)15;
+            a.off_lp = o; o += szl;
+            o = (o + 15) & ~(size_t)15;
+            a.off_cs = o; o += szc;
+            a.smem_total = o;
+            return true;
+        }
+        if (a.R <= 32) return false;
+        a.R /= 2;
+    }
+}
+
+int pad_chains(int C) { return C <= 4 ? 4 : (C <= 8 ? 8 : (C <= 16 ? 16 : 32)); }
+
+template <typename F>
+cudaError_t set_smem_attr(F f, size_t bytes) {
+    return cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
+}  // namespace
+
+extern "C" {
+
+int epg_upload_sites(epg_ctx* c, int model, int D, const int64_t* k_lim, const double* X, const int64_t* y,
+                     const int32_t* j_ind, const int32_t* Jk) {
+    if (!c->arr[EPG_Q]) return epg_fail_msg(c, "epg_upload_sites: call epg_init_state first");
+    if (model != EPG_M1B && model != EPG_M3B && model != EPG_M4B) return epg_fail_msg(c, "unknown model id");
+    if (D < 1 || D > 1000) return epg_fail_msg(c, "bad D");
+    if (model_dphi(model, D) != c->d) return epg_fail_msg(c, "dphi of the model does not match the state dimension");
+    if ((j_ind == nullptr) != (Jk == nullptr)) return epg_fail_msg(c, "j_ind and Jk must be given together");
+    EPG_CHECK(c, cudaStreamSynchronize(c->stream));
+    epg_sites_free(c);
+    epg_site_data* s = new epg_site_data();
+    c->sites = s;
+    const int K = c->K;
+    s->model = model; s->D = D; s->K = K;
+    int S = ((D + 1 + 3) / 4) * 4;
+    if (((S / 4) & 1) == 0) S += 4;            // S = 4 * odd: conflict-free 128-bit row reads
+    s->S = S;
+    s->h_row0.assign(k_lim, k_lim + K + 1);
+    const int64_t base = s->h_row0[0];
+    for (auto& v : s->h_row0) v -= base;
+    const int64_t N = s->h_row0[K];
+    s->N = N;
+    if (N < 1) return epg_fail_msg(c, "no rows");
+    // group structure
+    std::vector<int> gptr(K + 1, 0), grows;
+    s->h_J.resize(K); s->h_p.resize(K);
+    for (int k = 0; k < K; ++k) {
+        const int64_t lo = s->h_row0[k], hi = s->h_row0[k + 1];
+        if (hi <= lo) return epg_fail_msg(c, "empty site");
+        const int J = Jk ? Jk[k] : 1;
+        if (J < 1) return epg_fail_msg(c, "bad group count");
+        gptr[k] = (int)grows.size();
+        if (!j_ind) { grows.push_back(0); grows.push_back((int)(hi - lo)); }
+        else {
+            int64_t r = lo;
+            for (int j = 0; j < J; ++j) {
+                grows.push_back((int)(r - lo));
+                while (r < hi && j_ind[base + r] == j) ++r;
+            }
+            if (r != hi) return epg_fail_msg(c, "j_ind must be sorted and in [0, J) within every site");
+            grows.push_back((int)(hi - lo));
+        }
+        s->h_J[k] = J;
+        s->h_p[k] = model_np(model, D, J);
+        s->Pmax = std::max(s->Pmax, s->h_p[k]);
+        s->Jmax = std::max(s->Jmax, J);
+        s->max_rows = std::max<int64_t>(s->max_rows, hi - lo);
+    }
+    gptr[K] = (int)grows.size();
+    s->Pmax = (s->Pmax + 31) & ~31;
+    EPG_CHECK(c, cudaMalloc((void**)&s->X, sizeof(float) * (size_t)N * S));
+    EPG_CHECK(c, cudaMalloc((void**)&s->y, sizeof(float) * (size_t)N));
+    EPG_CHECK(c, cudaMalloc((void**)&s->row0, sizeof(int64_t) * (K + 1)));
+    EPG_CHECK(c, cudaMalloc((void**)&s->grp_ptr, sizeof(int) * (K + 1)));
+    EPG_CHECK(c, cudaMalloc((void**)&s->grp_rows, sizeof(int) * grows.size()));
+    EPG_CHECK(c, cudaMemcpyAsync(s->row0, s->h_row0.data(), sizeof(int64_t) * (K + 1), cudaMemcpyHostToDevice, c->stream));
+    EPG_CHECK(c, cudaMemcpyAsync(s->grp_ptr, gptr.data(), sizeof(int) * (K + 1), cudaMemcpyHostToDevice, c->stream));
+    EPG_CHECK(c, cudaMemcpyAsync(s->grp_rows, grows.data(), sizeof(int) * grows.size(), cudaMemcpyHostToDevice, c->stream));
+    // X, y: staged fp64 -> fp32 conversion in chunks
+    const int64_t chunk_rows = std::max<int64_t>(1, (int64_t)(128u << 20) / (sizeof(double) * D));
+    double* stage = nullptr;
+    EPG_CHECK(c, cudaMalloc((void**)&stage, sizeof(double) * (size_t)chunk_rows * D));
+    for (int64_t r = 0; r < N; r += chunk_rows) {
+        const int64_t rows = std::min(chunk_rows, N - r);
+        EPG_CHECK(c, cudaMemcpyAsync(stage, X + (size_t)(base + r) * D, sizeof(double) * (size_t)rows * D,
+                                     cudaMemcpyHostToDevice, c->stream));
+        const int64_t tot = rows * S;
+        k_convert_x<<<(unsigned)((tot + 255) / 256), 256, 0, c->stream>>>(stage, s->X + (size_t)r * S, rows, D, S);
+        c->launches++;
+        EPG_CHECK(c, cudaStreamSynchronize(c->stream));
+    }
+    {
+        int64_t* ys = reinterpret_cast<int64_t*>(stage);
+        const int64_t ychunk = chunk_rows * D;    // same bytes
+        for (int64_t r = 0; r < N; r += ychunk) {
+            const int64_t rows = std::min(ychunk, N - r);
+            EPG_CHECK(c, cudaMemcpyAsync(ys, y + base + r, sizeof(int64_t) * (size_t)rows, cudaMemcpyHostToDevice, c->stream));
+            k_convert_y<<<(unsigned)((rows + 255) / 256), 256, 0, c->stream>>>(ys, s->y + r, rows);
+            c->launches++;
+            EPG_CHECK(c, cudaStreamSynchronize(c->stream));
+        }
+    }
+    EPG_CHECK(c, cudaFree(stage));
+    EPG_CHECK(c, cudaGetLastError());
+    return 0;
+}
+
+int epg_num_params(epg_ctx* c, int k) {
+    if (!c->sites || k < 0 || k >= c->K) return -1;
+    return c->sites->h_p[k];
+}
+
+static int fill_args(epg_ctx* c, SamplerArgs& a, int C, int CP) {
+    epg_site_data* s = c->sites;
+    a.X = s->X; a.y = s->y; a.row0 = s->row0; a.grp_ptr = s->grp_ptr; a.grp_rows = s->grp_rows;
+    a.model = s->model; a.D = s->D; a.S = s->S; a.d = c->d;
+    a.cavQ = c->arr[EPG_CAVQ]; a.cavm = c->arr[EPG_CAVM];
+    a.P = s->Pmax; a.C = C;
+    const size_t need = sizeof(float) * (size_t)c->K * C * NVEC * s->Pmax;
+    if (need > s->chain_mem_bytes) {
+        if (s->chain_mem) cudaFree(s->chain_mem);
+        s->chain_mem = nullptr; s->chain_mem_bytes = 0;
+        EPG_CHECK(c, cudaMalloc((void**)&s->chain_mem, need));
+        s->chain_mem_bytes = need;
+    }
+    const size_t need_lq = sizeof(float) * (size_t)c->K * C * s->Pmax;
+    if (need_lq > s->last_q_bytes || s->last_C != C) {
+        if (s->last_q) cudaFree(s->last_q);
+        s->last_q = nullptr; s->last_q_bytes = 0;
+        EPG_CHECK(c, cudaMalloc((void**)&s->last_q, need_lq));
+        EPG_CHECK(c, cudaMemsetAsync(s->last_q, 0, need_lq, c->stream));
+        s->last_q_bytes = need_lq; s->last_C = C;
+    }
+    EPG_CHECK(c, epg_reserve((void**)&s->omega, &s->omega_bytes, sizeof(float) * (size_t)c->K * c->d * c->d));
+    EPG_CHECK(c, epg_reserve((void**)&s->out, &s->out_bytes, sizeof(double) * (size_t)c->K * 4 + sizeof(uint32_t) * c->K));
+    a.chain_mem = s->chain_mem; a.last_q = s->last_q; a.omega = s->omega; a.out = s->out;
+    if (!plan_smem(a, CP, s->max_rows, c->d)) return epg_fail_msg(c, "sampler: shapes exceed the shared-memory plan");
+    return 0;
+}
+
+int epg_reserve_draws(epg_ctx* c, int n);
+
+int epg_tilted_sample(epg_ctx* c, int k0, int k1, const uint32_t* seeds, const epg_sampler_opts* o,
+                      double* msteps_out, double* mrhat_out, int64_t* n_leapfrog_out, double* seconds) {
+    if (!c->sites) return epg_fail_msg(c, "epg_tilted_sample: no site data (epg_upload_sites)");
+    if (k0 < 0 || k1 > c->K || k0 >= k1 || !seeds || !o) return epg_fail_msg(c, "epg_tilted_sample: bad args");
+    if (o->chains < 1 || o->chains > 32) return epg_fail_msg(c, "chains must be in 1..32");
+    if (o->thin != 1) return epg_fail_msg(c, "only thin=1 is supported");
+    if (o->iter < 1) return epg_fail_msg(c, "iter must be positive");
+    const int warm = o->warmup < 0 ? o->iter / 2 : o->warmup;
+    if (warm >= o->iter) return epg_fail_msg(c, "warmup must be smaller than iter");
+    const int C = o->chains, CP = pad_chains(C);
+    const int n = C * (o->iter - warm);
+    epg_site_data* s = c->sites;
+    if (o->init_mode == 2 && (s->last_C != C || !s->last_q)) return epg_fail_msg(c, "init_prev without previous draws");
+    if (int rc = epg_reserve_draws(c, n)) return rc;
+    SamplerArgs a;
+    memset(&a, 0, sizeof(a));
+    if (int rc = fill_args(c, a, C, CP)) return rc;
+    a.iter = o->iter; a.warmup = warm; a.init_mode = o->init_mode;
+    a.max_depth = o->max_treedepth > 0 ? std::min(o->max_treedepth, MAXDEPTH_CAP) : 10;
+    a.delta = o->adapt_delta > 0 ? o->adapt_delta : 0.8;
+    // Stan 2.17 windowed_adaptation defaults (75 / 50 / 25) and their rescaling
+    a.win_init = 75; a.win_term = 50; a.win_base = 25;
+    if (warm >= 20 && a.win_init + a.win_base + a.win_term > warm) {
+        a.win_init = (int)(0.15 * warm); a.win_term = (int)(0.1 * warm);
+        a.win_base = warm - (a.win_init + a.win_term);
+    }
+    uint32_t* dseeds = reinterpret_cast<uint32_t*>(s->out + (size_t)c->K * 4);
+    EPG_CHECK(c, cudaMemcpyAsync(dseeds, seeds, sizeof(uint32_t) * (k1 - k0), cudaMemcpyHostToDevice, c->stream));
+    a.seeds = dseeds;
+    a.draws = c->draws; a.n_draws = n; a.k0 = k0;
+    cudaEvent_t e0, e1;
+    EPG_CHECK(c, cudaEventCreate(&e0));
+    EPG_CHECK(c, cudaEventCreate(&e1));
+    EPG_CHECK(c, cudaEventRecord(e0, c->stream));
+#define LAUNCH_NUTS(CPV)                                                          \
+    {                                                                             \
+        EPG_CHECK(c, set_smem_attr(k_nuts<CPV>, a.smem_total));                   \
+        k_nuts<CPV><<<k1 - k0, NTHR, a.smem_total, c->stream>>>(a);               \
+    }
+    if (CP == 4) LAUNCH_NUTS(4) else if (CP == 8) LAUNCH_NUTS(8) else if (CP == 16) LAUNCH_NUTS(16) else LAUNCH_NUTS(32)
+    c->launches++;
+    EPG_CHECK(c, cudaGetLastError());
+    EPG_CHECK(c, cudaEventRecord(e1, c->stream));
+    EPG_CHECK(c, cudaEventSynchronize(e1));
+    float ms = 0.f;
+    EPG_CHECK(c, cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (seconds) *seconds = ms * 1e-3;
+    std::vector<double> out((size_t)(k1 - k0) * 4);
+    EPG_CHECK(c, cudaMemcpyAsync(out.data(), s->out + (size_t)k0 * 4, sizeof(double) * out.size(),
+                                 cudaMemcpyDeviceToHost, c->stream));
+    EPG_CHECK(c, cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < k1 - k0; ++i) {
+        if (msteps_out) msteps_out[i] = out[4 * i + 0];
+        if (mrhat_out) mrhat_out[i] = out[4 * i + 1];
+        if (n_leapfrog_out) n_leapfrog_out[i] = (int64_t)out[4 * i + 2];
+    }
+    return 0;
+}
+
+int epg_logdensity(epg_ctx* c, int k, int nq, const double* q, double* lp_out, double* grad_out) {
+    if (!c->sites || k < 0 || k >= c->K || nq < 1) return epg_fail_msg(c, "epg_logdensity: bad args");
+    epg_site_data* s = c->sites;
+    const int p = s->h_p[k];
+    const int C = 32, CP = 32;
+    SamplerArgs a;
+    memset(&a, 0, sizeof(a));
+    if (int rc = fill_args(c, a, C, CP)) return rc;
+    s->last_C = 0;                                   // chain memory was repurposed
+    a.k0 = k;
+    const size_t need = sizeof(double) * ((size_t)C * p * 2 + C);
+    EPG_CHECK(c, epg_reserve((void**)&s->ld_buf, &s->ld_bytes, need));
+    double* dq = s->ld_buf; double* dlp = dq + (size_t)C * p; double* dg = dlp + C;
+    EPG_CHECK(c, set_smem_attr(k_logdensity<32>, a.smem_total));
+    for (int q0 = 0; q0 < nq; q0 += C) {
+        const int nb = std::min(C, nq - q0);
+        EPG_CHECK(c, cudaMemcpyAsync(dq, q + (size_t)q0 * p, sizeof(double) * (size_t)nb * p, cudaMemcpyHostToDevice, c->stream));
+        k_set_q<<<(nb * p + 255) / 256, 256, 0, c->stream>>>(s->chain_mem, k * C, s->Pmax, p, nb, dq);
+        k_logdensity<32><<<1, NTHR, a.smem_total, c->stream>>>(a, nb, dlp, dg);
+        c->launches += 2;
+        EPG_CHECK(c, cudaGetLastError());
+        EPG_CHECK(c, cudaMemcpyAsync(lp_out + q0, dlp, sizeof(double) * nb, cudaMemcpyDeviceToHost, c->stream));
+        EPG_CHECK(c, cudaMemcpyAsync(grad_out + (size_t)q0 * p, dg, sizeof(double) * (size_t)nb * p, cudaMemcpyDeviceToHost, c->stream));
+        EPG_CHECK(c, cudaStreamSynchronize(c->stream));
+    }
+    return 0;
+}
+
+}  // extern "C"

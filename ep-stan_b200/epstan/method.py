@@ -490,6 +490,9 @@ class Master(object):
             else:
                 self.Qi[np.arange(d), np.arange(d), :] = self.K / (kwargs['init_site'] ** 2)
         self.iter = 0
+        # when True, run() leaves the state on the GPU between calls: the host
+        # mirrors are neither uploaded first nor refreshed afterwards (sync_host())
+        self.keep_on_device = False
 
         # shard + device context
         self.comm = self._comm_factory()
@@ -575,6 +578,10 @@ class Master(object):
         if self.comm.size > 1:
             return self.comm.allreduce_scalar(1.0 if flag else 0.0, 'min') > 0.5
         return bool(flag)
+
+    def sync_host(self):
+        """Refresh every host mirror (Q, r, Qi, ... workers' Mat/vec) from the device."""
+        self._pull_state()
 
     def cur_approx(self):
         """Current posterior approximation moments ``(S, m)`` (method.py:884-896)."""
@@ -682,7 +689,8 @@ class Master(object):
         othertimes = np.zeros(niter)
 
         def result(info):
-            self._pull_state()
+            if not self.keep_on_device:
+                self._pull_state()
             out = [info]
             if calc_moments:
                 out.append((m_phi_s, cov_phi_s))
@@ -690,7 +698,8 @@ class Master(object):
                 out.append((stimes, msteps, mrhats, othertimes))
             return tuple(out) if len(out) > 1 else out[0]
 
-        self._push_state(with_cavity=True)
+        if not self.keep_on_device:
+            self._push_state(with_cavity=True)
         local_workers = self.workers[sh.k_begin:sh.k_end]
 
         for cur_iter in range(niter):

@@ -84,11 +84,19 @@ class TiltedDensity(object):
             beta = phi[:, None, 2:2 + D] + etb * sig_b[:, None, :]
         alpha = (mu_a[:, None] if self.model == 'm4b' else 0.0) + eta * sig_a[:, None]   # (nq,J)
         # f[q,n] = alpha[q, j(n)] + x_n . beta[q, j(n)]
-        f = alpha[:, self.j_ind] + np.einsum('nd,qnd->qn', self.X, beta[:, self.j_ind, :])
-        lp_lik = np.sum(self.y * f - np.logaddexp(0.0, f), axis=1)
-        e = self.y - 1.0 / (1.0 + np.exp(-f))                      # (nq,N)
-        s = e @ self.G.T                                           # (nq,J) per-group sum of e
-        g = np.einsum('qn,jn,nd->qjd', e, self.G, self.X)          # (nq,J,D) per-group X'e
+        if J == 1:
+            f = alpha + beta[:, 0, :] @ self.X.T                       # BLAS path (single group)
+        else:
+            f = alpha[:, self.j_ind] + np.einsum('nd,qnd->qn', self.X, beta[:, self.j_ind, :])
+        with np.errstate(over='ignore', invalid='ignore'):
+            lp_lik = np.sum(self.y * f - np.logaddexp(0.0, f), axis=1)
+            e = self.y - 1.0 / (1.0 + np.exp(-f))                      # (nq,N)
+        if J == 1:
+            s = e.sum(axis=1, keepdims=True)
+            g = (e @ self.X)[:, None, :]
+        else:
+            s = e @ self.G.T                                           # (nq,J) per-group sum of e
+            g = np.einsum('qn,jn,nd->qjd', e, self.G, self.X)          # (nq,J,D) per-group X'e
         dev = phi - self.mu
         c = dev @ self.Omega.T                                     # Omega symmetric
         lp = -0.5 * np.sum(dev * c, axis=1) - 0.5 * np.sum(eta ** 2, axis=1) + lp_lik

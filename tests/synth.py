@@ -1,0 +1,28 @@
+"""Small synthetic hierarchical logistic-regression problems for the tests."""
+import numpy as np
+
+from oracle import density as dens
+from oracle import fakes
+
+
+def make_site(model, n, D, J, seed):
+    """One site's data + a plausible cavity.  Returns dict(X, y, j_ind, J, mu, Omega)."""
+    rng = np.random.RandomState(seed)
+    X = rng.standard_normal((n, D)) * 0.7 + 0.2 * rng.standard_normal(D)
+    sizes = np.full(J, n // J)
+    sizes[:n - sizes.sum()] += 1
+    j_ind = np.repeat(np.arange(J), sizes)
+    beta = rng.standard_normal(D) * 0.8
+    alpha = rng.standard_normal(J) * 0.7
+    bj = np.repeat(beta[None, :], J, axis=0) + (0.0 if model == 'm1b' else 0.4 * rng.standard_normal((J, D)))
+    f = alpha[j_ind] + np.einsum('nd,nd->n', X, bj[j_ind])
+    y = (rng.uniform(size=n) < 1 / (1 + np.exp(-f))).astype(np.int64)
+    d = dens.dphi(model, D)
+    Omega = fakes.random_spd(rng, d, scale=1.5)
+    mu = 0.3 * rng.standard_normal(d)
+    return dict(X=X, y=y, j_ind=j_ind, J=J, mu=mu, Omega=Omega, d=d, sizes=sizes)
+
+
+def oracle_density(model, site):
+    return dens.TiltedDensity(model, site['X'], site['y'], site['mu'], site['Omega'],
+                              j_ind=site['j_ind'], J=site['J'])
