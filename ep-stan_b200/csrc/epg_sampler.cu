@@ -158,8 +158,9 @@ struct ChainS {
     double eps_sum;
     long long n_leap_total;
     int n_div;
-    double stack_lsw[MAXDEPTH_CAP], stack_V[MAXDEPTH_CAP];
 };
+// per-level scalars of the tree stack live in shared memory next to ChainS
+struct ChainStack { double lsw[MAXDEPTH_CAP], V[MAXDEPTH_CAP]; };
 
 struct SamplerArgs {
     // site data
@@ -193,8 +194,16 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
-__device__ __forceinline__ float softplus_f(float f) { return fmaxf(f, 0.0f) + log1pf(__expf(-fabsf(f))); }
-__device__ __forceinline__ float sigmoid_f(float f) { return 1.0f / (1.0f + __expf(-f)); }
+// Bernoulli-logit pieces from ONE exp, ONE log and ONE reciprocal:
+//   t = exp(-|f|);  softplus(f) = max(f,0) + log(1+t);  sigmoid(f) = f>=0 ? 1/(1+t) : t/(1+t)
+// returns y*f - softplus(f) and writes e = y - sigmoid(f)
+__device__ __forceinline__ float logit_terms(float f, float yv, float& e) {
+    const float t = __expf(-fabsf(f));
+    const float inv = __frcp_rn(1.0f + t);
+    const float sg = f >= 0.0f ? inv : t * inv;
+    e = yv - sg;
+    return yv * f - (fmaxf(f, 0.0f) + __logf(1.0f + t));
+}
 
 // ---------------------------------------------------------------------------
 // Likelihood pass for all chains of one site: fills V_GL (likelihood part of
@@ -302,8 +311,9 @@ __device__ void likelihood_pass(const SamplerArgs& a, unsigned char* smem, int s
                 const float yv = a.y[row_begin + r0 + tid];
 #pragma unroll
                 for (int c = 0; c < CP; ++c) {
-                    lpacc[c] += yv * f[c] - softplus_f(f[c]);
-                    f[c] = yv - sigmoid_f(f[c]);
+                    float e;
+                    lpacc[c] += logit_terms(f[c], yv, e);
+                    f[c] = e;
                 }
 #pragma unroll
                 for (int c4 = 0; c4 < CP / 4; ++c4)
@@ -406,6 +416,7 @@ struct ChainCtx {
     uint2 key;
     const float* omega;   // [d*d] fp32 cavity precision
     const double* mu;     // [d]
+    ChainStack* stk;      // shared memory
     __device__ float* v(int which) const { return cvec(a, cg, which); }
 };
 
@@ -717,7 +728,7 @@ __device__ void chain_step(const ChainCtx& x, ChainS& s, double lp_lik, int c_lo
     while ((s.nleaf >> l) & 1) {
         // merge the pending left sibling at level l with the node just completed
         const int base = V_STACK + 4 * l;
-        const double lsw_sub = log_sum_exp(s.stack_lsw[l], s.cur_lsw);
+        const double lsw_sub = log_sum_exp(x.stk->lsw[l], s.cur_lsw);
         bool take_right = s.cur_lsw > lsw_sub;
         if (!take_right) take_right = rng_uniform(x.key, s.rng) < (float)exp(s.cur_lsw - lsw_sub);
         const float* lpsl = x.v(base + 0); const float* lrho = x.v(base + 1);
@@ -736,7 +747,7 @@ __device__ void chain_step(const ChainCtx& x, ChainS& s, double lp_lik, int c_lo
         if (!take_right) {
             vcopy(x, V_QPROP, base + 2);
             vcopy(x, V_GPROP, base + 3);
-            s.Vprop = s.stack_V[l];
+            s.Vprop = x.stk->V[l];
         }
         __syncwarp();
         s.cur_lsw = lsw_sub;
@@ -750,8 +761,7 @@ __device__ void chain_step(const ChainCtx& x, ChainS& s, double lp_lik, int c_lo
         const int base = V_STACK + 4 * l;
         vcopy(x, base + 0, V_CPSL); vcopy(x, base + 1, V_CRHO);
         vcopy(x, base + 2, V_QPROP); vcopy(x, base + 3, V_GPROP);
-        s.stack_lsw[l] = s.cur_lsw;
-        s.stack_V[l] = s.Vprop;
+        if (x.lane == 0) { x.stk->lsw[l] = s.cur_lsw; x.stk->V[l] = s.Vprop; }
         __syncwarp();
         s.nleaf += 1;
         issue_leapfrog(x, s);
@@ -801,6 +811,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_nuts(const SamplerArgs a) {
     const int J = a.grp_ptr[k_local + 1] - a.grp_ptr[k_local] - 1;
     const int p = model_np(a.model, D, J);
     ChainS* cs = reinterpret_cast<ChainS*>(smem + a.off_cs);
+    ChainStack* cstk = reinterpret_cast<ChainStack*>(smem + a.off_cs + sizeof(ChainS) * 32);
     __shared__ double lp_lik[32];
     __shared__ int n_active;
 
@@ -842,8 +853,8 @@ __global__ void __launch_bounds__(NTHR, 1) k_nuts(const SamplerArgs a) {
         // ---- per-chain state machines ----
         for (int c = warp; c < C; c += NWARP) {
             ChainCtx x{a, k_local * C + c, p, d, J, D, lane, make_uint2(site_seed, (uint32_t)c),
-                       om, a.cavm + (size_t)k_local * d};
-            ChainS s = cs[c];
+                       om, a.cavm + (size_t)k_local * d, cstk + c};
+            ChainS s = cs[c];                  // private copy: every lane runs the same scalar code
             const int before = s.phase;
             chain_step(x, s, lp_lik[c], c, k_local);
             __syncwarp();
@@ -945,7 +956,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_logdensity(const SamplerArgs a, int
     __syncthreads();
     likelihood_pass<CP>(a, smem, k_local, k_local, nq, J, row_begin, n_rows, grows, lp_lik);
     for (int c = warp; c < nq; c += NWARP) {
-        ChainCtx x{a, k_local * a.C + c, p, d, J, D, lane, make_uint2(0u, 0u), om, a.cavm + (size_t)k_local * d};
+        ChainCtx x{a, k_local * a.C + c, p, d, J, D, lane, make_uint2(0u, 0u), om, a.cavm + (size_t)k_local * d, nullptr};
         const double V = finish_gradient(x, lp_lik[c]);
         const float* g = x.v(V_G);
         if (lane == 0) lp_out[c] = -V;
@@ -977,7 +988,7 @@ bool plan_smem(SamplerArgs& a, int CP, int64_t max_rows, int d) {
         const size_t szG = sizeof(float) * (size_t)a.slices * CP * S;
         const size_t szg = sizeof(float) * (size_t)CP * d;
         const size_t szl = sizeof(double) * (size_t)NWARP * CP;
-        const size_t szc = sizeof(ChainS) * 32;
+        const size_t szc = (sizeof(ChainS) + sizeof(ChainStack)) * 32;
         size_t rest = fixed + szB + szG + ((szg + 15) & ~(size_t)15) + szl + szc + 64;
         const size_t xres = sizeof(float) * (size_t)max_rows * S;
         size_t xbytes;

@@ -493,6 +493,7 @@ class Master(object):
         # when True, run() leaves the state on the GPU between calls: the host
         # mirrors are neither uploaded first nor refreshed afterwards (sync_host())
         self.keep_on_device = False
+        self.n_leapfrog_total = 0     # gradient evaluations spent by the built-in sampler (local sites)
 
         # shard + device context
         self.comm = self._comm_factory()
@@ -614,6 +615,7 @@ class Master(object):
                 w.last_time, w.last_msteps, w.last_mrhat = secs, float(msteps[i]), float(mrhat[i])
                 w.last_n_leapfrog = int(nleap[i])
                 w._have_prev = True
+            self.n_leapfrog_total += int(np.sum(nleap))
             if save_last_param and 'phi' in save_last_param:
                 dr = ctx.get_draws(n)
                 for i, w in enumerate(workers):

@@ -292,3 +292,52 @@ def test_damp_sweep(ep, K, d):
     assert relerr(mse[good], omse[good]) < TOL
     assert relerr(kl[good], okl[good]) < TOL
     ctx.close()
+
+
+@pytest.mark.parametrize('tag,seed,n,d', gi.CV_CASES)
+def test_cv_moments_vs_reference(ep, golden, tag, seed, n, d):
+    """a8: util.cv_moments (control-variate moments) against the reference's outputs."""
+    g = golden['cv']
+    c = gi.cv_case(seed, n, d)
+    Q2, r2 = orc.invert_normal_params(c['S2'], c['m2'])
+    # the d2 x d2 Gram system is ill-conditioned: LU-vs-LU agreement is limited by
+    # cond * eps (the pinned oracle itself only reaches 1e-7 against the reference here)
+    tol = 1e-9 if d <= 4 else 1e-6
+    for mcv in (True, False):
+        t = '%s_%s' % (tag, 'multi' if mcv else 'single')
+        S, m, used = ep.util.cv_moments(c['samp'].copy(), c['lp'], Q2, r2, multiple_cv=mcv)
+        assert used == bool(g['cv_%s_used' % t])
+        assert relerr(m, g['cv_%s_m' % t]) < tol
+        assert relerr(S, g['cv_%s_S' % t]) < tol
+        assert np.array_equal(S, S.T)
+    Q3, r3 = orc.invert_normal_params(c['S2'], c['m3'])
+    S, m, used = ep.util.cv_moments(c['samp'].copy(), c['lp'], Q3, r3)
+    assert used is False
+    assert relerr(m, g['cv_%s_fallback_m' % tag]) < TOL
+    assert relerr(S, g['cv_%s_fallback_S' % tag]) < TOL
+
+
+def test_cv_moments_batched_config2(ep):
+    """config 2 shape: K=64 sites, n=800, d=20 in one batched call vs the oracle."""
+    from epstan import _lib
+    K, n, d = 64, 800, 20
+    rng = np.random.RandomState(77)
+    draws = np.empty((K, d, n)); lps = np.empty((K, n)); Qt = np.empty((K, d, d)); rt = np.empty((K, d))
+    cases = []
+    from scipy.stats import multivariate_normal
+    for k in range(K):
+        S1 = fakes.random_spd(rng, d); m1 = rng.standard_normal(d)
+        S2 = S1 + 0.1 * fakes.random_spd(rng, d); m2 = m1 + 0.1 * rng.standard_normal(d)
+        samp = m1 + rng.standard_normal((n, d)) @ np.linalg.cholesky(S1).T
+        lp = multivariate_normal(mean=m1, cov=S1).logpdf(samp)
+        Q2, r2 = orc.invert_normal_params(S2, m2)
+        draws[k], lps[k], Qt[k], rt[k] = samp.T, lp, Q2, r2
+        cases.append((samp, lp, Q2, r2))
+    ctx = _lib.Context(0)
+    for mcv in (True, False):
+        S, m, used = ctx.cv_moments(draws, lps, Qt, rt, multiple_cv=mcv, regulate_a=0.9, max_a=5.0)
+        for k in (0, 17, 63):
+            oS, om, oused = orc.cv_moments(*cases[k], multiple_cv=mcv, regulate_a=0.9, max_a=5.0)
+            assert bool(used[k]) == oused
+            assert relerr(m[k], om) < 1e-6 and relerr(S[k], oS) < 1e-6
+    ctx.close()
