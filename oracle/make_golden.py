@@ -228,11 +228,28 @@ def gen_misc(ep, out):
         out['dg_%s_jind' % tag] = j_ind_k
 
 
+def gen_models(ep, out):
+    """experiment/models/m{1,3,4}b.py simulators and priors (small shapes)."""
+    import importlib
+    for name in ('m1b', 'm3b', 'm4b'):
+        mod = importlib.import_module('models.' + name)
+        for tag, kw, npg in (('corr', dict(Sigma_x='rand'), 5), ('iid', dict(), [3, 8])):
+            mdl = mod.model(6, 3, npg)
+            dat = mdl.simulate_data(rng=100, **kw)
+            key = 'mdl_%s_%s_' % (name, tag)
+            out[key + 'X'], out[key + 'y'], out[key + 'Nj'] = dat.X, dat.y, dat.Nj
+            out[key + 'phi'] = dat.true_values['phi']
+            out[key + 'unc'] = np.append(dat.calc_uncertainty()[0], dat.calc_uncertainty()[1])
+        S0, m0, Q0, r0 = mod.model(6, 3, 5).get_prior()
+        out['mdl_%s_Q0' % name], out['mdl_%s_r0' % name] = Q0, r0
+
+
 def main():
     ep = import_reference()
     os.makedirs(OUT, exist_ok=True)
     for name, fn in (('linalg', gen_linalg), ('worker', gen_worker),
-                     ('master', gen_master), ('cv', gen_cv), ('misc', gen_misc)):
+                     ('master', gen_master), ('cv', gen_cv), ('misc', gen_misc),
+                     ('models', gen_models)):
         out = {}
         fn(ep, out)
         path = os.path.join(OUT, name + '.npz')

@@ -36,7 +36,7 @@ def pytest_collection_modifyitems(config, items):
 @pytest.fixture(scope='session')
 def golden():
     return {name: np.load(os.path.join(GOLDEN, name + '.npz'))
-            for name in ('linalg', 'worker', 'master', 'cv', 'misc')}
+            for name in ('linalg', 'worker', 'master', 'cv', 'misc', 'models')}
 
 
 def relerr(a, b):

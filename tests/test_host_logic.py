@@ -1,0 +1,95 @@
+"""Host-side pieces of the drop-in package that need no GPU: the data
+simulators and priors of experiment/models (same seed -> the reference's data),
+distribute_groups, fit-object readers, model-name resolution, and the C ABI
+surface (the library loads and exports every symbol include/epgpu.h declares)."""
+import os
+import re
+import sys
+
+import numpy as np
+import pytest
+
+import golden_inputs as gi
+from oracle import fakes
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXP = os.path.join(ROOT, 'ep-stan_b200', 'experiment')
+
+
+def test_model_simulators_match_reference(golden):
+    if EXP not in sys.path:
+        sys.path.insert(0, EXP)
+    import importlib
+    g = golden['models']
+    for name in ('m1b', 'm3b', 'm4b'):
+        mod = importlib.import_module('models.' + name)
+        for tag, kw, npg in (('corr', dict(Sigma_x='rand'), 5), ('iid', dict(), [3, 8])):
+            dat = mod.model(6, 3, npg).simulate_data(rng=100, **kw)
+            key = 'mdl_%s_%s_' % (name, tag)
+            assert np.allclose(dat.X, g[key + 'X'], rtol=1e-12, atol=1e-13)
+            assert np.array_equal(dat.y, g[key + 'y']) and np.array_equal(dat.Nj, g[key + 'Nj'])
+            assert np.allclose(dat.true_values['phi'], g[key + 'phi'])
+            unc = dat.calc_uncertainty()
+            assert np.allclose(np.append(unc[0], unc[1]), g[key + 'unc'])
+        S0, m0, Q0, r0 = mod.model(6, 3, 5).get_prior()
+        assert np.allclose(Q0, g['mdl_%s_Q0' % name]) and np.allclose(r0, g['mdl_%s_r0' % name])
+        assert np.allclose(S0 @ Q0, np.eye(Q0.shape[0]))
+
+
+def test_distribute_groups(golden):
+    from epstan.util import distribute_groups
+    g = golden['misc']
+    cases = (('const', 64, 4, 20), ('const32', 64, 32, 20),
+             ('ragged', 40, 7, np.random.RandomState(52).randint(5, 40, size=40)),
+             ('ragged2', 33, 32, np.random.RandomState(53).randint(1, 9, size=33)))
+    for tag, J, K, Nj in cases:
+        Nk, Njk, jind = distribute_groups(J, K, Nj)
+        assert np.array_equal(Nk, g['dg_%s_Nk' % tag])
+        assert np.array_equal(Njk, g['dg_%s_Njk' % tag])
+        assert np.array_equal(jind, g['dg_%s_jind' % tag]) and jind.dtype == np.int32
+    Nj, a, b = distribute_groups(5, 5, 3)
+    assert a is None and b is None and np.array_equal(Nj, [3] * 5)
+    Nk, ppg, _ = distribute_groups(3, 5, np.array([10, 4, 7]))
+    assert Nk.sum() == 21 and len(Nk) == 5 and ppg.sum() == 5
+    with pytest.raises(ValueError):
+        distribute_groups(3, 1, 4)
+    with pytest.raises(ValueError):
+        distribute_groups(2, 100, 3)
+
+
+def test_fit_readers_and_model_names():
+    from epstan import util
+    rng = np.random.RandomState(0)
+    x = rng.standard_normal((12, 3))
+    fitobj = fakes.FakeFit(x, chains=3, niter=8, warmup=4)
+    out = util.copy_fit_samples(fitobj, 'phi')
+    assert out.flags['F_CONTIGUOUS'] and np.array_equal(out, x)
+    last = util.get_last_fit_sample(fitobj)
+    assert len(last) == 3 and np.array_equal(last[1]['phi'], x[7])
+    m = util.load_stan('/some/path/models/m4b_sg.stan')
+    assert m.family == 'm4b' and m.single_group and m.dphi(16) == 34
+    assert util.load_stan('m1b.pkl').dphi(19) == 20 and not util.load_stan('m3b').single_group
+    with pytest.raises(ValueError):
+        util.load_stan('m2a')
+
+
+def test_c_abi_surface():
+    """The library loads without a device and exports every declared symbol; a
+    context cannot be created on a machine without a GPU (no CPU fallback)."""
+    from epstan import _lib
+    lib = _lib.load()
+    header = open(os.path.join(ROOT, 'include', 'epgpu.h')).read()
+    declared = set(re.findall(r'\b(epg_[a-z_0-9]+)\s*\(', header))
+    bound = {name for name, _, _ in _lib.SYMBOLS}
+    assert declared == bound, declared ^ bound
+    for name in declared:
+        assert hasattr(lib, name)
+    assert lib.epg_version() == 1
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    if not has_gpu:
+        with pytest.raises(_lib.EpgError):
+            _lib.Context(0)
