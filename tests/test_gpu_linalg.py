@@ -106,7 +106,8 @@ def build_master(ep, sc):
         m.Qi[:, :, 1] = -4.0 * np.eye(d)
         m.Q[:] = m.Q0 + m.Qi.sum(axis=2)
         for k, w in enumerate(m.workers):
-            w.cavity(m.Q, m.r, m.Qi[:, :, k], m.ri[:, k])
+            if m._shard.k_begin <= k < m._shard.k_end:      # (multi-rank runs: local sites only)
+                w.cavity(m.Q, m.r, m.Qi[:, :, k], m.ri[:, k])
             w.phase = 1
     return m
 
