@@ -231,6 +231,9 @@ def main():
 
     import torch
     import torch.distributed as dist
+    if os.environ.get('BENCH_DEBUG'):
+        import faulthandler
+        faulthandler.dump_traceback_later(int(os.environ['BENCH_DEBUG']), exit=True)
     world = int(os.environ.get('WORLD_SIZE', 1))
     rank = int(os.environ.get('RANK', 0))
     local_rank = int(os.environ.get('LOCAL_RANK', 0))
@@ -238,7 +241,9 @@ def main():
         raise SystemExit("bench.py: no CUDA device (there is no CPU fallback)")
     torch.cuda.set_device(local_rank)
     if world > 1:
-        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+        import datetime
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank),
+                                timeout=datetime.timedelta(seconds=int(os.environ.get('BENCH_NCCL_TIMEOUT', 600))))
     import epstan.method as method
     from epstan import _lib
     method.set_default_stream(torch.cuda.current_stream().cuda_stream)

@@ -65,7 +65,7 @@ extern "C" {
 
 int epg_version(void) { return EPG_VERSION; }
 
-int epg_create(epg_ctx** out, int device, void* stream) {
+int epg_create(epg_ctx** out, int device, void* stream, int own_stream) {
     if (!out) return -2;
     *out = nullptr;
     int ndev = 0;
@@ -74,7 +74,7 @@ int epg_create(epg_ctx** out, int device, void* stream) {
     if (cudaSetDevice(device) != cudaSuccess) return -1;
     epg_ctx* c = new epg_ctx();
     c->device = device;
-    if (stream) { c->stream = (cudaStream_t)stream; c->own_stream = false; }
+    if (!own_stream) { c->stream = (cudaStream_t)stream; c->own_stream = false; }
     else {
         if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return -1; }
         c->own_stream = true;

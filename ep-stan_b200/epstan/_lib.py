@@ -38,7 +38,7 @@ _lib = None
 # every symbol include/epgpu.h declares: (name, restype, argtypes)
 SYMBOLS = [
     ('epg_version', C.c_int, []),
-    ('epg_create', C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_void_p]),
+    ('epg_create', C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.c_int]),
     ('epg_destroy', None, [C.c_void_p]),
     ('epg_last_error', C.c_char_p, [C.c_void_p]),
     ('epg_sync', C.c_int, [C.c_void_p]),
@@ -106,7 +106,9 @@ class Context:
     def __init__(self, device=0, stream=None):
         self._lib = load()
         h = C.c_void_p()
-        rc = self._lib.epg_create(C.byref(h), int(device), C.c_void_p(stream) if stream else None)
+        # stream None -> private stream; an int (0 == the default stream) -> caller's stream
+        own = stream is None
+        rc = self._lib.epg_create(C.byref(h), int(device), None if own else C.c_void_p(int(stream)), int(own))
         if rc != 0 or not h:
             raise EpgError("epg_create failed on device {}: no usable CUDA device "
                            "(libepgpu has no CPU fallback)".format(device))

@@ -68,9 +68,12 @@ enum epg_prec_estim { EPG_PREC_SAMPLE = 0, EPG_PREC_OLSE = 1 };  /* method.py:16
 
 /* ---- lifetime ---- */
 int epg_version(void);
-/* device: CUDA ordinal; stream: a cudaStream_t to run on (e.g. torch's current
- * stream) or NULL for a private non-blocking stream. */
-int epg_create(epg_ctx** out, int device, void* stream);
+/* device: CUDA ordinal.  own_stream != 0: the context creates a private
+ * non-blocking stream (`stream` is ignored).  own_stream == 0: every kernel and
+ * copy is issued on the caller's cudaStream_t `stream` (NULL = the legacy
+ * default stream) -- required when the caller interleaves its own work, e.g.
+ * NCCL collectives issued by torch.distributed on torch's current stream. */
+int epg_create(epg_ctx** out, int device, void* stream, int own_stream);
 void epg_destroy(epg_ctx* ctx);
 const char* epg_last_error(const epg_ctx* ctx);
 int epg_sync(epg_ctx* ctx);
