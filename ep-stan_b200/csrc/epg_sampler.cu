@@ -26,7 +26,12 @@
 // fp64 for the energies used in the accept/multinomial weights.
 #include "epg_internal.h"
 #include "epg_common.cuh"
+#include <cuda.h>
+#include <cuda_bf16.h>
 #include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
 #include <vector>
 
 #define NTHR 256
@@ -42,6 +47,10 @@ struct epg_site_data {
     int K = 0;
     int64_t N = 0;
     float* X = nullptr;                 // [N][S]
+    __nv_bfloat16* Xb = nullptr;        // [N][64] bf16 copy for the tensor-core pass (column D = 1)
+    CUtensorMap tmap;                   // TMA descriptor of Xb: box 64 x 128 rows, 128-byte swizzle
+    bool tc_ok = false;                 // tensor-core pass usable (single group, D+1 <= 64)
+    int use_tc = 1;                     // option (epg_set_option "use_tc")
     float* y = nullptr;                 // [N]
     int64_t* row0 = nullptr;            // [K+1]
     int* grp_ptr = nullptr;             // [K+1] offsets into grp_rows
@@ -67,7 +76,7 @@ struct epg_site_data {
 void epg_sites_free(epg_ctx* c) {
     epg_site_data* s = c->sites;
     if (!s) return;
-    cudaFree(s->X); cudaFree(s->y); cudaFree(s->row0); cudaFree(s->grp_ptr); cudaFree(s->grp_rows);
+    cudaFree(s->X); cudaFree(s->Xb); cudaFree(s->y); cudaFree(s->row0); cudaFree(s->grp_ptr); cudaFree(s->grp_rows);
     cudaFree(s->chain_mem); cudaFree(s->last_q); cudaFree(s->omega); cudaFree(s->out); cudaFree(s->ld_buf);
     delete s;
     c->sites = nullptr;
@@ -86,6 +95,13 @@ __global__ void k_convert_x(const double* __restrict__ src, float* __restrict__ 
     const int64_t r = idx / S;
     const int c = (int)(idx - r * S);
     dst[idx] = c < D ? (float)src[r * D + c] : (c == D ? 1.0f : 0.0f);
+}
+__global__ void k_convert_xb(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t rows, int S) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= rows * 64) return;
+    const int64_t r = idx >> 6;
+    const int c = (int)(idx & 63);
+    dst[idx] = __float2bfloat16(c < S ? src[r * S + c] : 0.0f);
 }
 __global__ void k_convert_y(const int64_t* __restrict__ src, float* __restrict__ dst, int64_t n) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -122,21 +138,26 @@ __device__ __forceinline__ float rng_normal(uint2 key, uint32_t ctr, uint32_t el
 __device__ __forceinline__ double log_sum_exp(double a, double b) {
     if (a == -INFINITY) return b;
     if (b == -INFINITY) return a;
+    // the correction term is < log 2: single precision is ample for it
     const double m = fmax(a, b);
-    return m + log1p(exp(-fabs(a - b)));
+    return m + (double)log1pf(__expf(-(float)fabs(a - b)));
 }
 
-// per-chain vectors in global memory (stride P floats)
+// per-chain vectors (stride P floats).  The first `hot_nvec` of them (ordered by
+// how often a tick touches them) live in shared memory, the rest in global memory.
 enum {
-    V_Q = 0, V_P, V_G,            // working point z
-    V_QM, V_PM, V_GM,             // minus end of the trajectory
-    V_QP, V_PP, V_GP,             // plus end
+    V_Q = 0,                      // working point z: position
+    V_GL,                         // likelihood-gradient output of the batched pass
+    V_G, V_P,                     // working point: gradient of the potential, momentum
+    V_MINV,                       // inverse metric (diag)
+    V_CRHO, V_CPSL,               // node being built: rho and left-end p_sharp
+    V_QPROP, V_GPROP,             // proposal of the node being built
     V_RHO,                        // sum of momenta over the trajectory
     V_QS, V_GS,                   // current sample
-    V_QPROP, V_GPROP,             // proposal of the node being built
-    V_CRHO, V_CPSL,               // node being built: rho and left-end p_sharp
-    V_MINV, V_WMEAN, V_WM2,       // inverse metric (diag), Welford accumulators
-    V_GL,                         // likelihood-gradient output of the batched pass
+    V_QM, V_PM, V_GM,             // minus end of the trajectory
+    V_QP, V_PP, V_GP,             // plus end
+    V_NHOT,                       // ---- vectors below are always in global memory ----
+    V_WMEAN = V_NHOT, V_WM2,      // Welford accumulators
     V_RS0, V_RQ0, V_RS1, V_RQ1,   // split-Rhat sums / sums of squares per half
     V_STACK                       // + 4*level : psl, rho, qprop, gprop
 };
@@ -176,14 +197,20 @@ struct SamplerArgs {
     const uint32_t* seeds;
     // outputs
     double* draws; int n_draws;     // [K][d][n]
-    double* out;                    // [K][4]: mean eps, max rhat, n_leapfrog, n_divergent
+    double* out;                    // [K][8]: mean eps, max rhat, n_leapfrog, n_divergent, clk chain, clk lik, ticks, -
     int k0;
     // shared-memory plan
     int R, resident, slices, NC, combos;
-    size_t off_E, off_B, off_G, off_gphi, off_lp, off_cs, smem_total;
+    int use_tc, hot_nvec, omega_smem;
+    size_t off_E, off_B, off_G, off_gphi, off_lp, off_cs, off_hot, off_omega, smem_total;
 };
 
 __device__ __forceinline__ float* cvec(const SamplerArgs& a, int chain_global, int v) {
+    if (v < a.hot_nvec) {
+        extern __shared__ __align__(1024) unsigned char smem_dyn[];
+        const int c_local = chain_global - (a.k0 + (int)blockIdx.x) * a.C;
+        return reinterpret_cast<float*>(smem_dyn + a.off_hot) + ((size_t)c_local * a.hot_nvec + v) * a.P;
+    }
     return a.chain_mem + ((size_t)chain_global * NVEC + v) * a.P;
 }
 
@@ -199,11 +226,13 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 // returns y*f - softplus(f) and writes e = y - sigmoid(f)
 __device__ __forceinline__ float logit_terms(float f, float yv, float& e) {
     const float t = __expf(-fabsf(f));
-    const float inv = __frcp_rn(1.0f + t);
+    const float inv = __fdividef(1.0f, 1.0f + t);
     const float sg = f >= 0.0f ? inv : t * inv;
     e = yv - sg;
     return yv * f - (fmaxf(f, 0.0f) + __logf(1.0f + t));
 }
+
+#include "epg_lik_tc.cuh"
 
 // ---------------------------------------------------------------------------
 // Likelihood pass for all chains of one site: fills V_GL (likelihood part of
@@ -407,6 +436,93 @@ __device__ void likelihood_pass(const SamplerArgs& a, unsigned char* smem, int s
 }
 
 // ---------------------------------------------------------------------------
+// Tensor-core variant of the likelihood pass (single-group sites, D+1 <= 64,
+// <= 16 chains): see epg_lik_tc.cuh.  Same outputs as likelihood_pass.
+// ---------------------------------------------------------------------------
+__device__ void likelihood_pass_tc(const SamplerArgs& a, unsigned char* smem, unsigned char* tcb, uint32_t tmem_base,
+                                   const CUtensorMap* tmap, tc::State& st, int k_local, int nchains,
+                                   int64_t row_begin, int n_rows, double* lp_out) {
+    const int tid = threadIdx.x;
+    const bool worker = tid < NTHR;                  // warps 8, 9 only drive TMA / MMA inside the pass
+    const int D = a.D, d = a.d, model = a.model;
+    float* gphi = reinterpret_cast<float*>(smem + a.off_gphi);
+    double* lpw = reinterpret_cast<double*>(smem + a.off_lp);       // [NWARP][8]
+    const int chain0 = k_local * a.C;
+    const int ia = (model == EPG_M4B) ? 1 : 0;
+    const int ib = (model == EPG_M4B) ? 2 + D : 1;
+    PROF_T(q0);
+    if (worker) {
+        for (int e = tid; e < tc::NCH * d; e += NTHR) gphi[e] = 0.0f;
+        // coefficient operands B = B_hi + B_lo (bf16 each), K-major interleaved layout
+        for (int e = tid; e < tc::NCH * tc::KW; e += NTHR) {
+            const int c = e / tc::KW, col = e - c * tc::KW;
+            float v = 0.0f;
+            if (c < nchains && col <= D) {
+                const float* q = cvec(a, chain0 + c, V_Q);
+                if (col == D) v = q[d] * __expf(q[ia]) + (model == EPG_M4B ? q[0] : 0.0f);
+                else if (model == EPG_M1B) v = q[1 + col];
+                else v = q[d + 1 + col] * __expf(q[ib + col]) + (model == EPG_M4B ? q[2 + col] : 0.0f);
+            }
+            const __nv_bfloat16 hi = __float2bfloat16(v);
+            const __nv_bfloat16 lo = __float2bfloat16(v - __bfloat162float(hi));
+            const int cc = tc::chain_col(c);
+            *reinterpret_cast<__nv_bfloat16*>(tcb + tc::Smem::BM + tc::interleave_off32(cc, col)) = hi;
+            *reinterpret_cast<__nv_bfloat16*>(tcb + tc::Smem::BM + tc::interleave_off32(tc::NCH + cc, col)) = lo;
+        }
+        tc::fence_proxy_async();
+    }
+    __syncthreads();
+    PROF_T(q1);
+    const int ksteps = (D + 1 + 15) / 16;           // 16 input columns per tcgen05.mma
+    if (nchains <= 4) tc::pass<2>(tcb, tmem_base, tmap, st, row_begin, n_rows, ksteps, a.y, lpw);
+    else if (nchains <= 8) tc::pass<4>(tcb, tmem_base, tmap, st, row_begin, n_rows, ksteps, a.y, lpw);
+    else tc::pass<8>(tcb, tmem_base, tmap, st, row_begin, n_rows, ksteps, a.y, lpw);
+    PROF_T(q2);
+    __syncthreads();
+    PROF_T(q3);
+    if (worker) {
+        const float* gout = reinterpret_cast<const float*>(tcb + tc::Smem::GOUT);
+        for (int e = tid; e < tc::NCH * tc::KW; e += NTHR) {
+            const int c = e / tc::KW, col = e - c * tc::KW;
+            if (c >= nchains || col > D) continue;
+            const float gsum = gout[tc::chain_col(c) * tc::KW + col];
+            const float* q = cvec(a, chain0 + c, V_Q);
+            float* gl = cvec(a, chain0 + c, V_GL);
+            if (col == D) {
+                const float sa = __expf(q[ia]);
+                gl[d] = sa * gsum;
+                gphi[c * d + ia] += sa * q[d] * gsum;
+                if (model == EPG_M4B) gphi[c * d + 0] += gsum;
+            } else if (model == EPG_M1B) {
+                gphi[c * d + 1 + col] += gsum;
+            } else {
+                const float sb = __expf(q[ib + col]);
+                const float etb = q[d + 1 + col];
+                gl[d + 1 + col] = sb * gsum;
+                gphi[c * d + ib + col] += sb * etb * gsum;
+                if (model == EPG_M4B) gphi[c * d + 2 + col] += gsum;
+            }
+        }
+        if (tid < nchains) {
+            // chain c lives in half (c & 1), slot (c >> 1): warps 4*half .. 4*half+3
+            const int half = tid & 1, slot = tid >> 1;
+            double sum = 0.0;
+            for (int w = 4 * half; w < 4 * half + 4; ++w) sum += lpw[w * (tc::NCH / 2) + slot];
+            lp_out[tid] = sum;
+        }
+    }
+    __syncthreads();
+    if (worker)
+        for (int e = tid; e < tc::NCH * d; e += NTHR) {
+            const int c = e / d, i = e - c * d;
+            if (c < nchains) cvec(a, chain0 + c, V_GL)[i] = gphi[e];
+        }
+    __syncthreads();
+    PROF_T(q4);
+    if (threadIdx.x == 0) { PROF2_ADD(2, q0, q1); PROF2_ADD(3, q1, q2); PROF2_ADD(4, q2, q3); PROF2_ADD(5, q3, q4); PROF2_ADD(6, 0, 1); }
+}
+
+// ---------------------------------------------------------------------------
 // per-chain (one warp) helpers
 // ---------------------------------------------------------------------------
 struct ChainCtx {
@@ -415,7 +531,7 @@ struct ChainCtx {
     int p, d, J, D, lane;
     uint2 key;
     const float* omega;   // [d*d] fp32 cavity precision
-    const double* mu;     // [d]
+    const float* muf;     // [d] fp32 cavity mean
     ChainStack* stk;      // shared memory
     __device__ float* v(int which) const { return cvec(a, cg, which); }
 };
@@ -443,8 +559,8 @@ __device__ double finish_gradient(const ChainCtx& x, double lp_lik) {
     float quad = 0.0f, sq = 0.0f;
     for (int i = x.lane; i < d; i += 32) {
         float ci = 0.0f;
-        for (int j = 0; j < d; ++j) ci = fmaf(x.omega[i + (size_t)j * d], q[j] - (float)x.mu[j], ci);
-        quad += ci * (q[i] - (float)x.mu[i]);
+        for (int j = 0; j < d; ++j) ci = fmaf(x.omega[i + (size_t)j * d], q[j] - x.muf[j], ci);
+        quad += ci * (q[i] - x.muf[i]);
         g[i] = ci - gl[i];
     }
     for (int i = d + x.lane; i < x.p; i += 32) {
@@ -704,7 +820,7 @@ __device__ void chain_step(const ChainCtx& x, ChainS& s, double lp_lik, int c_lo
     if (isnan(h)) h = INFINITY;
     s.n_leap_tr += 1;
     const double dH = s.H0 - h;
-    s.sum_metro += (dH > 0.0) ? 1.0 : exp(dH);
+    s.sum_metro += (dH > 0.0) ? 1.0 : (double)__expf((float)dH);
     if (-dH > 1000.0) {                 // divergent: the subtree is discarded
         s.n_div += 1;
         end_transition(x, s, c_local, site_draw);
@@ -730,7 +846,7 @@ __device__ void chain_step(const ChainCtx& x, ChainS& s, double lp_lik, int c_lo
         const int base = V_STACK + 4 * l;
         const double lsw_sub = log_sum_exp(x.stk->lsw[l], s.cur_lsw);
         bool take_right = s.cur_lsw > lsw_sub;
-        if (!take_right) take_right = rng_uniform(x.key, s.rng) < (float)exp(s.cur_lsw - lsw_sub);
+        if (!take_right) take_right = rng_uniform(x.key, s.rng) < __expf((float)(s.cur_lsw - lsw_sub));
         const float* lpsl = x.v(base + 0); const float* lrho = x.v(base + 1);
         float* crho = x.v(V_CRHO); float* cpsl = x.v(V_CPSL);
         const float* p = x.v(V_P); const float* minv = x.v(V_MINV);
@@ -772,7 +888,7 @@ __device__ void chain_step(const ChainCtx& x, ChainS& s, double lp_lik, int c_lo
     else            { vcopy(x, V_QM, V_Q); vcopy(x, V_PM, V_P); vcopy(x, V_GM, V_G); }
     s.depth += 1;
     bool take = s.cur_lsw > s.lsw;
-    if (!take) take = rng_uniform(x.key, s.rng) < (float)exp(s.cur_lsw - s.lsw);
+    if (!take) take = rng_uniform(x.key, s.rng) < __expf((float)(s.cur_lsw - s.lsw));
     if (take) { vcopy(x, V_QS, V_QPROP); vcopy(x, V_GS, V_GPROP); s.Vs = s.Vprop; }
     s.lsw = log_sum_exp(s.lsw, s.cur_lsw);
     __syncwarp();
@@ -800,8 +916,8 @@ __device__ void chain_step(const ChainCtx& x, ChainS& s, double lp_lik, int c_lo
 // the persistent sampling kernel: one CTA per site
 // ---------------------------------------------------------------------------
 template <int CP>
-__global__ void __launch_bounds__(NTHR, 1) k_nuts(const SamplerArgs a) {
-    extern __shared__ __align__(16) unsigned char smem[];
+__global__ void __launch_bounds__(tc::NTHREADS, 1) k_nuts(const SamplerArgs a, const __grid_constant__ CUtensorMap tmap) {
+    extern __shared__ __align__(1024) unsigned char smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int k_local = a.k0 + blockIdx.x;
     const int C = a.C, d = a.d, D = a.D, S = a.S;
@@ -815,18 +931,31 @@ __global__ void __launch_bounds__(NTHR, 1) k_nuts(const SamplerArgs a) {
     __shared__ double lp_lik[32];
     __shared__ int n_active;
 
+    // (the tensor-core variant runs with two extra warps, 8 = TMA and 9 = MMA issue,
+    //  which take part only in the barriers and in tc::pass)
+    const bool worker = tid < NTHR;
     // cavity precision -> fp32 copy (read by every chain every tick)
-    float* om = a.omega + (size_t)k_local * d * d;
+    float* om = a.omega_smem ? reinterpret_cast<float*>(smem + a.off_omega)
+                             : a.omega + (size_t)k_local * (d * d + d);
+    float* muf = om + d * d;
     const double* cq = a.cavQ + (size_t)k_local * d * d;
-    for (int e = tid; e < d * d; e += NTHR) om[e] = (float)cq[e];
+    if (worker) {
+        for (int e = tid; e < d * d; e += NTHR) om[e] = (float)cq[e];
+        for (int i = tid; i < d; i += NTHR) muf[i] = (float)a.cavm[(size_t)k_local * d + i];
+    }
     // resident design matrix
-    if (a.resident) {
+    if (a.resident && !a.use_tc) {
         const float4* src = reinterpret_cast<const float4*>(a.X + (size_t)row_begin * S);
         float4* dst = reinterpret_cast<float4*>(smem);
         for (int e = tid; e < n_rows * (S >> 2); e += NTHR) dst[e] = src[e];
     }
+    // tensor-core pass: barriers + tensor memory
+    unsigned char* tcb = smem + ((1024u - (tc::smem_u32(smem) & 1023u)) & 1023u);
+    uint32_t tmem_base = 0;
+    tc::State tcst;
+    if (a.use_tc) tmem_base = tc::setup(tcb);
     // chain state
-    for (int c = warp; c < C; c += NWARP) {
+    for (int c = warp; worker && c < C; c += NWARP) {
         ChainS& s = cs[c];
         const int cg = k_local * C + c;
         if (lane == 0) {
@@ -849,11 +978,13 @@ __global__ void __launch_bounds__(NTHR, 1) k_nuts(const SamplerArgs a) {
     __syncthreads();
 
     const uint32_t site_seed = a.seeds[blockIdx.x];
+    long long clk_chain = 0, clk_lik = 0, n_ticks = 0;
     for (;;) {
+        const long long tk0 = clock64();
         // ---- per-chain state machines ----
-        for (int c = warp; c < C; c += NWARP) {
+        for (int c = warp; worker && c < C; c += NWARP) {
             ChainCtx x{a, k_local * C + c, p, d, J, D, lane, make_uint2(site_seed, (uint32_t)c),
-                       om, a.cavm + (size_t)k_local * d, cstk + c};
+                       om, muf, cstk + c};
             ChainS s = cs[c];                  // private copy: every lane runs the same scalar code
             const int before = s.phase;
             chain_step(x, s, lp_lik[c], c, k_local);
@@ -867,8 +998,14 @@ __global__ void __launch_bounds__(NTHR, 1) k_nuts(const SamplerArgs a) {
         __threadfence_block();
         __syncthreads();
         if (n_active <= 0) break;
-        likelihood_pass<CP>(a, smem, k_local, k_local, C, J, row_begin, n_rows, grows, lp_lik);
+        const long long tk1 = clock64();
+        if (a.use_tc) likelihood_pass_tc(a, smem, tcb, tmem_base, &tmap, tcst, k_local, C, row_begin, n_rows, lp_lik);
+        else likelihood_pass<CP>(a, smem, k_local, k_local, C, J, row_begin, n_rows, grows, lp_lik);
+        clk_chain += tk1 - tk0;
+        clk_lik += clock64() - tk1;
+        ++n_ticks;
     }
+    if (a.use_tc) tc::teardown(tmem_base);
 
     // ---- per-site analytics: mean step size, max split-Rhat, leapfrogs ----
     __syncthreads();
@@ -922,7 +1059,8 @@ __global__ void __launch_bounds__(NTHR, 1) k_nuts(const SamplerArgs a) {
                 nd += cs[c].n_div;
                 if (cs[c].phase == PH_DONE) { eps_mean += cs[c].eps_sum / (per > 0 ? per : 1); ++ok; }
             }
-            double* o = a.out + (size_t)k_local * 4;
+            double* o = a.out + (size_t)k_local * 8;
+            o[4] = (double)clk_chain; o[5] = (double)clk_lik; o[6] = (double)n_ticks; o[7] = 0.0;
             o[0] = ok ? eps_mean / ok : NAN;
             o[1] = (ok == C) ? (double)worst : NAN;
             o[2] = nl;
@@ -933,8 +1071,9 @@ __global__ void __launch_bounds__(NTHR, 1) k_nuts(const SamplerArgs a) {
 
 // log-density / gradient at caller-supplied points (parity tests)
 template <int CP>
-__global__ void __launch_bounds__(NTHR, 1) k_logdensity(const SamplerArgs a, int nq, double* lp_out, double* grad_out) {
-    extern __shared__ __align__(16) unsigned char smem[];
+__global__ void __launch_bounds__(tc::NTHREADS, 1) k_logdensity(const SamplerArgs a, const __grid_constant__ CUtensorMap tmap,
+                                                           int nq, double* lp_out, double* grad_out) {
+    extern __shared__ __align__(1024) unsigned char smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int k_local = a.k0;
     const int d = a.d, D = a.D, S = a.S;
@@ -944,24 +1083,47 @@ __global__ void __launch_bounds__(NTHR, 1) k_logdensity(const SamplerArgs a, int
     const int J = a.grp_ptr[k_local + 1] - a.grp_ptr[k_local] - 1;
     const int p = model_np(a.model, D, J);
     __shared__ double lp_lik[32];
-    float* om = a.omega + (size_t)k_local * d * d;
+    const bool worker = tid < NTHR;
+    float* om = a.omega_smem ? reinterpret_cast<float*>(smem + a.off_omega)
+                             : a.omega + (size_t)k_local * (d * d + d);
+    float* muf = om + d * d;
     const double* cq = a.cavQ + (size_t)k_local * d * d;
-    for (int e = tid; e < d * d; e += NTHR) om[e] = (float)cq[e];
-    if (a.resident) {
+    if (worker) {
+        for (int e = tid; e < d * d; e += NTHR) om[e] = (float)cq[e];
+        for (int i = tid; i < d; i += NTHR) muf[i] = (float)a.cavm[(size_t)k_local * d + i];
+    }
+    if (a.resident && !a.use_tc) {
         const float4* src = reinterpret_cast<const float4*>(a.X + (size_t)row_begin * S);
         float4* dst = reinterpret_cast<float4*>(smem);
         for (int e = tid; e < n_rows * (S >> 2); e += NTHR) dst[e] = src[e];
     }
+    unsigned char* tcb = smem + ((1024u - (tc::smem_u32(smem) & 1023u)) & 1023u);
+    uint32_t tmem_base = 0;
+    tc::State tcst;
+    if (a.use_tc) tmem_base = tc::setup(tcb);
+    // the evaluation points were staged in the global copy of V_Q (k_set_q)
+    if (worker && a.hot_nvec > V_Q)
+        for (int e = tid; e < nq * a.P; e += NTHR) {
+            const int c = e / a.P, i = e - c * a.P;
+            cvec(a, k_local * a.C + c, V_Q)[i] = a.chain_mem[((size_t)(k_local * a.C + c) * NVEC + V_Q) * a.P + i];
+        }
     __threadfence_block();
     __syncthreads();
-    likelihood_pass<CP>(a, smem, k_local, k_local, nq, J, row_begin, n_rows, grows, lp_lik);
-    for (int c = warp; c < nq; c += NWARP) {
-        ChainCtx x{a, k_local * a.C + c, p, d, J, D, lane, make_uint2(0u, 0u), om, a.cavm + (size_t)k_local * d, nullptr};
+    if (a.use_tc) {
+        likelihood_pass_tc(a, smem, tcb, tmem_base, &tmap, tcst, k_local, nq, row_begin, n_rows, lp_lik);
+        // second evaluation: exercises the pipeline state carried across ticks
+        likelihood_pass_tc(a, smem, tcb, tmem_base, &tmap, tcst, k_local, nq, row_begin, n_rows, lp_lik);
+    } else {
+        likelihood_pass<CP>(a, smem, k_local, k_local, nq, J, row_begin, n_rows, grows, lp_lik);
+    }
+    for (int c = warp; worker && c < nq; c += NWARP) {
+        ChainCtx x{a, k_local * a.C + c, p, d, J, D, lane, make_uint2(0u, 0u), om, muf, nullptr};
         const double V = finish_gradient(x, lp_lik[c]);
         const float* g = x.v(V_G);
         if (lane == 0) lp_out[c] = -V;
         for (int i = lane; i < p; i += 32) grad_out[(size_t)c * p + i] = -(double)g[i];
     }
+    if (a.use_tc) tc::teardown(tmem_base);
 }
 
 __global__ void k_set_q(float* chain_mem, int chain0, int P, int p, int nq, const double* q) {
@@ -974,37 +1136,60 @@ __global__ void k_set_q(float* chain_mem, int chain0, int P, int p, int nq, cons
 // shared-memory plan for a launch
 bool plan_smem(SamplerArgs& a, int CP, int64_t max_rows, int d) {
     const size_t budget = 227 * 1024 - 1024;
+    auto al16 = [](size_t v) { return (v + 15) & ~(size_t)15; };
+    const size_t sz_cs = al16((sizeof(ChainS) + sizeof(ChainStack)) * 32);
+    const size_t sz_om = al16(sizeof(float) * ((size_t)d * d + d));
+    const size_t per_vec = sizeof(float) * (size_t)a.C * a.P;          // one hot vector of every chain
+    // tail regions shared by both variants: [omega][hot vectors]
+    auto place_tail = [&](size_t o) -> size_t {
+        a.omega_smem = 0; a.hot_nvec = 0; a.off_omega = a.off_hot = 0;
+        if (o + sz_om <= budget && sz_om <= 48 * 1024) { a.omega_smem = 1; a.off_omega = o; o += sz_om; }
+        int nv = per_vec ? (int)((budget - o) / per_vec) : 0;
+        if (nv > V_NHOT) nv = V_NHOT;
+        if (nv > 0) { a.hot_nvec = nv; a.off_hot = o; o += al16((size_t)nv * per_vec); }
+        return o;
+    };
+    if (a.use_tc) {
+        size_t o = al16(1024 + tc::Smem::TOTAL);      // 1024: alignment slack for the swizzled tiles
+        a.off_E = a.off_B = a.off_G = 0;
+        a.R = 0; a.resident = 0; a.slices = 1; a.NC = 1; a.combos = 1;
+        a.off_gphi = o; o += al16(sizeof(float) * (size_t)tc::NCH * d);
+        a.off_lp = o; o += al16(sizeof(double) * (size_t)NWARP * tc::NCH);
+        a.off_cs = o; o += sz_cs;
+        if (o > budget) return false;
+        a.smem_total = place_tail(o);
+        return true;
+    }
     const int S = a.S;
     const int S4 = S / 4;
     a.combos = S4 * (CP / 4);
     if (a.combos <= NTHR) { a.NC = 1; a.slices = NTHR / a.combos; if (a.slices > 16) a.slices = 16; }
     else { a.NC = (a.combos + NTHR - 1) / NTHR; a.slices = 1; if (a.NC > NCMAX) return false; }
     a.R = NTHR;
+    // what we would like to keep on chip besides the design matrix
+    const size_t want_tail = sz_om + al16((size_t)V_NHOT * per_vec);
     for (;;) {
-        size_t fixed = 0;
-        fixed += sizeof(float) * (size_t)a.R * CP;                       // E
-        fixed = (fixed + 15) & ~(size_t)15;
-        const size_t szB = sizeof(float) * (size_t)CP * S;
-        const size_t szG = sizeof(float) * (size_t)a.slices * CP * S;
-        const size_t szg = sizeof(float) * (size_t)CP * d;
-        const size_t szl = sizeof(double) * (size_t)NWARP * CP;
-        const size_t szc = (sizeof(ChainS) + sizeof(ChainStack)) * 32;
-        size_t rest = fixed + szB + szG + ((szg + 15) & ~(size_t)15) + szl + szc + 64;
-        const size_t xres = sizeof(float) * (size_t)max_rows * S;
+        const size_t szE = al16(sizeof(float) * (size_t)a.R * CP);
+        const size_t szB = al16(sizeof(float) * (size_t)CP * S);
+        const size_t szG = al16(sizeof(float) * (size_t)a.slices * CP * S);
+        const size_t szg = al16(sizeof(float) * (size_t)CP * d);
+        const size_t szl = al16(sizeof(double) * (size_t)NWARP * CP);
+        const size_t rest = szE + szB + szG + szg + szl + sz_cs;
+        const size_t xres = al16(sizeof(float) * (size_t)max_rows * S);
+        const size_t xstream = al16(2 * sizeof(float) * (size_t)a.R * S);
         size_t xbytes;
-        if (xres + rest <= budget) { a.resident = 1; xbytes = xres; }
-        else { a.resident = 0; xbytes = 2 * sizeof(float) * (size_t)a.R * S; }
-        xbytes = (xbytes + 15) & ~(size_t)15;
+        // the resident design matrix wins over the hot chain vectors only if both fit
+        if (xres + rest + (want_tail <= 96 * 1024 ? want_tail : 0) <= budget) { a.resident = 1; xbytes = xres; }
+        else { a.resident = 0; xbytes = xstream; }
         if (xbytes + rest <= budget) {
             size_t o = xbytes;
-            a.off_E = o; o += fixed;
+            a.off_E = o; o += szE;
             a.off_B = o; o += szB;
             a.off_G = o; o += szG;
-            a.off_gphi = o; o += (szg + 15) & ~(size_t)15;
+            a.off_gphi = o; o += szg;
             a.off_lp = o; o += szl;
-            o = (o + 15) & ~(size_t)15;
-            a.off_cs = o; o += szc;
-            a.smem_total = o;
+            a.off_cs = o; o += sz_cs;
+            a.smem_total = place_tail(o);
             return true;
         }
         if (a.R <= 32) return false;
@@ -1106,7 +1291,43 @@ int epg_upload_sites(epg_ctx* c, int model, int D, const int64_t* k_lim, const d
     }
     EPG_CHECK(c, cudaFree(stage));
     EPG_CHECK(c, cudaGetLastError());
+    // tensor-core path: bf16 copy [N][64] + TMA descriptor (single-group sites, D+1 <= 64)
+    s->tc_ok = false;
+    memset(&s->tmap, 0, sizeof(s->tmap));
+    if (s->Jmax == 1 && D + 1 <= tc::KW) {
+        EPG_CHECK(c, cudaMalloc((void**)&s->Xb, sizeof(__nv_bfloat16) * (size_t)N * tc::KW));
+        const int64_t tot = N * tc::KW;
+        k_convert_xb<<<(unsigned)((tot + 255) / 256), 256, 0, c->stream>>>(s->X, s->Xb, N, S);
+        c->launches++;
+        EPG_CHECK(c, cudaStreamSynchronize(c->stream));
+        typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                      const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                      CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        EPG_CHECK(c, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (fn && qres == cudaDriverEntryPointSuccess) {
+            const cuuint64_t gdim[2] = {(cuuint64_t)tc::KW, (cuuint64_t)N};
+            const cuuint64_t gstride[1] = {(cuuint64_t)tc::KW * 2};
+            const cuuint32_t box[2] = {(cuuint32_t)tc::KW, (cuuint32_t)tc::TILE_M};
+            const cuuint32_t estr[2] = {1, 1};
+            const CUresult r = ((encode_fn)fn)(&s->tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, s->Xb, gdim, gstride, box, estr,
+                                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            s->tc_ok = (r == CUDA_SUCCESS);
+        }
+    }
     return 0;
+}
+
+int epg_set_option(epg_ctx* c, const char* name, double value) {
+    if (!name) return epg_fail_msg(c, "epg_set_option: null name");
+    if (strcmp(name, "use_tc") == 0) {
+        if (!c->sites) return epg_fail_msg(c, "epg_set_option(use_tc): upload the sites first");
+        c->sites->use_tc = value != 0.0;
+        return 0;
+    }
+    return epg_fail_msg(c, std::string("epg_set_option: unknown option ") + name);
 }
 
 int epg_num_params(epg_ctx* c, int k) {
@@ -1135,9 +1356,10 @@ static int fill_args(epg_ctx* c, SamplerArgs& a, int C, int CP) {
         EPG_CHECK(c, cudaMemsetAsync(s->last_q, 0, need_lq, c->stream));
         s->last_q_bytes = need_lq; s->last_C = C;
     }
-    EPG_CHECK(c, epg_reserve((void**)&s->omega, &s->omega_bytes, sizeof(float) * (size_t)c->K * c->d * c->d));
-    EPG_CHECK(c, epg_reserve((void**)&s->out, &s->out_bytes, sizeof(double) * (size_t)c->K * 4 + sizeof(uint32_t) * c->K));
+    EPG_CHECK(c, epg_reserve((void**)&s->omega, &s->omega_bytes, sizeof(float) * (size_t)c->K * (c->d * c->d + c->d)));
+    EPG_CHECK(c, epg_reserve((void**)&s->out, &s->out_bytes, sizeof(double) * (size_t)c->K * 8 + sizeof(uint32_t) * c->K));
     a.chain_mem = s->chain_mem; a.last_q = s->last_q; a.omega = s->omega; a.out = s->out;
+    a.use_tc = (s->tc_ok && s->use_tc && C <= tc::NCH) ? 1 : 0;
     if (!plan_smem(a, CP, s->max_rows, c->d)) return epg_fail_msg(c, "sampler: shapes exceed the shared-memory plan");
     return 0;
 }
@@ -1170,7 +1392,7 @@ int epg_tilted_sample(epg_ctx* c, int k0, int k1, const uint32_t* seeds, const e
         a.win_init = (int)(0.15 * warm); a.win_term = (int)(0.1 * warm);
         a.win_base = warm - (a.win_init + a.win_term);
     }
-    uint32_t* dseeds = reinterpret_cast<uint32_t*>(s->out + (size_t)c->K * 4);
+    uint32_t* dseeds = reinterpret_cast<uint32_t*>(s->out + (size_t)c->K * 8);
     EPG_CHECK(c, cudaMemcpyAsync(dseeds, seeds, sizeof(uint32_t) * (k1 - k0), cudaMemcpyHostToDevice, c->stream));
     a.seeds = dseeds;
     a.draws = c->draws; a.n_draws = n; a.k0 = k0;
@@ -1181,7 +1403,7 @@ int epg_tilted_sample(epg_ctx* c, int k0, int k1, const uint32_t* seeds, const e
 #define LAUNCH_NUTS(CPV)                                                          \
     {                                                                             \
         EPG_CHECK(c, set_smem_attr(k_nuts<CPV>, a.smem_total));                   \
-        k_nuts<CPV><<<k1 - k0, NTHR, a.smem_total, c->stream>>>(a);               \
+        k_nuts<CPV><<<k1 - k0, a.use_tc ? tc::NTHREADS : NTHR, a.smem_total, c->stream>>>(a, s->tmap); \
     }
     if (CP == 4) LAUNCH_NUTS(4) else if (CP == 8) LAUNCH_NUTS(8) else if (CP == 16) LAUNCH_NUTS(16) else LAUNCH_NUTS(32)
     c->launches++;
@@ -1192,14 +1414,32 @@ int epg_tilted_sample(epg_ctx* c, int k0, int k1, const uint32_t* seeds, const e
     EPG_CHECK(c, cudaEventElapsedTime(&ms, e0, e1));
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     if (seconds) *seconds = ms * 1e-3;
-    std::vector<double> out((size_t)(k1 - k0) * 4);
-    EPG_CHECK(c, cudaMemcpyAsync(out.data(), s->out + (size_t)k0 * 4, sizeof(double) * out.size(),
+    std::vector<double> out((size_t)(k1 - k0) * 8);
+    EPG_CHECK(c, cudaMemcpyAsync(out.data(), s->out + (size_t)k0 * 8, sizeof(double) * out.size(),
                                  cudaMemcpyDeviceToHost, c->stream));
     EPG_CHECK(c, cudaStreamSynchronize(c->stream));
     for (int i = 0; i < k1 - k0; ++i) {
-        if (msteps_out) msteps_out[i] = out[4 * i + 0];
-        if (mrhat_out) mrhat_out[i] = out[4 * i + 1];
-        if (n_leapfrog_out) n_leapfrog_out[i] = (int64_t)out[4 * i + 2];
+        if (msteps_out) msteps_out[i] = out[8 * i + 0];
+        if (mrhat_out) mrhat_out[i] = out[8 * i + 1];
+        if (n_leapfrog_out) n_leapfrog_out[i] = (int64_t)out[8 * i + 2];
+    }
+#ifdef EPG_TC_PROFILE
+    if (getenv("EPGPU_TRACE")) {
+        long long hp[8];
+        cudaMemcpyFromSymbol(hp, tc::g_prof, sizeof(hp));
+        fprintf(stderr, "[epgpu] epilogue cycles/tile: wait_f %.0f ld %.0f math %.0f wait_e %.0f sts %.0f fence %.0f arrive %.0f (tiles %lld)\n",
+                (double)hp[0] / hp[7], (double)hp[1] / hp[7], (double)hp[2] / hp[7], (double)hp[3] / hp[7], (double)hp[4] / hp[7], (double)hp[5] / hp[7], (double)hp[6] / hp[7], hp[7]);
+        cudaMemcpyFromSymbol(hp, tc::g_prof2, sizeof(hp));
+        fprintf(stderr, "[epgpu] lik pass cycles/tick (thread 0): build %.0f pass %.0f sync %.0f chainrule+tail %.0f\n", (double)hp[2] / hp[6], (double)hp[3] / hp[6], (double)hp[4] / hp[6], (double)hp[5] / hp[6]);
+        fprintf(stderr, "[epgpu] mma thread cycles/tile: wait_e %.0f issue_g2 %.0f commits %.0f gemm1(wait full+issue) %.0f (tiles %lld)\n",
+                (double)hp[0] / hp[7], (double)hp[1] / hp[7], (double)hp[2] / hp[7], (double)hp[3] / hp[7], hp[7]);
+    }
+#endif
+    if (getenv("EPGPU_TRACE")) {
+        double cc = 0, cl = 0, nt = 0;
+        for (int i = 0; i < k1 - k0; ++i) { cc += out[8 * i + 4]; cl += out[8 * i + 5]; nt += out[8 * i + 6]; }
+        fprintf(stderr, "[epgpu] sampler %d sites: %.3f s, ticks/site %.0f, cycles/tick chain %.0f lik %.0f (tc=%d)\n",
+                k1 - k0, ms * 1e-3, nt / (k1 - k0), cc / nt, cl / nt, a.use_tc);
     }
     return 0;
 }
@@ -1208,7 +1448,7 @@ int epg_logdensity(epg_ctx* c, int k, int nq, const double* q, double* lp_out, d
     if (!c->sites || k < 0 || k >= c->K || nq < 1) return epg_fail_msg(c, "epg_logdensity: bad args");
     epg_site_data* s = c->sites;
     const int p = s->h_p[k];
-    const int C = 32, CP = 32;
+    const int C = (s->tc_ok && s->use_tc) ? tc::NCH : 32, CP = 32;
     SamplerArgs a;
     memset(&a, 0, sizeof(a));
     if (int rc = fill_args(c, a, C, CP)) return rc;
@@ -1222,7 +1462,7 @@ int epg_logdensity(epg_ctx* c, int k, int nq, const double* q, double* lp_out, d
         const int nb = std::min(C, nq - q0);
         EPG_CHECK(c, cudaMemcpyAsync(dq, q + (size_t)q0 * p, sizeof(double) * (size_t)nb * p, cudaMemcpyHostToDevice, c->stream));
         k_set_q<<<(nb * p + 255) / 256, 256, 0, c->stream>>>(s->chain_mem, k * C, s->Pmax, p, nb, dq);
-        k_logdensity<32><<<1, NTHR, a.smem_total, c->stream>>>(a, nb, dlp, dg);
+        k_logdensity<32><<<1, a.use_tc ? tc::NTHREADS : NTHR, a.smem_total, c->stream>>>(a, s->tmap, nb, dlp, dg);
         c->launches += 2;
         EPG_CHECK(c, cudaGetLastError());
         EPG_CHECK(c, cudaMemcpyAsync(lp_out + q0, dlp, sizeof(double) * nb, cudaMemcpyDeviceToHost, c->stream));

@@ -69,6 +69,7 @@ SYMBOLS = [
                                    _c_int32_p, _c_int32_p]),
     ('epg_tilted_sample', C.c_int, [C.c_void_p, C.c_int, C.c_int, _c_uint32_p, C.POINTER(SamplerOpts),
                                     _c_double_p, _c_double_p, _c_int64_p, _c_double_p]),
+    ('epg_set_option', C.c_int, [C.c_void_p, C.c_char_p, C.c_double]),
     ('epg_num_params', C.c_int, [C.c_void_p, C.c_int]),
     ('epg_logdensity', C.c_int, [C.c_void_p, C.c_int, C.c_int, _c_double_p, _c_double_p, _c_double_p]),
 ]
@@ -302,6 +303,9 @@ class Context:
             self._h, k0, k1, seeds.ctypes.data_as(_c_uint32_p), C.byref(opts), _dp(msteps), _dp(mrhat),
             nleap.ctypes.data_as(_c_int64_p), C.byref(secs)))
         return msteps, mrhat, nleap, secs.value
+
+    def set_option(self, name, value):
+        self._ck(self._lib.epg_set_option(self._h, name.encode(), float(value)))
 
     def num_params(self, k):
         return int(self._lib.epg_num_params(self._h, k))

@@ -176,6 +176,11 @@ int epg_tilted_sample(epg_ctx* ctx, int k0, int k1, const uint32_t* seeds,
                       const epg_sampler_opts* opts, double* msteps_out, double* mrhat_out,
                       int64_t* n_leapfrog_out, double* seconds);
 
+/* Options.  "use_tc" (default 1): use the tcgen05/TMA likelihood pass when the
+ * shapes allow it (single-group sites, D+1 <= 64, chains <= 16); 0 forces the
+ * fp32 SIMT pass.  Call after epg_upload_sites. */
+int epg_set_option(epg_ctx* ctx, const char* name, double value);
+
 /* Direct evaluation of the tilted log-density and its gradient for site k at
  * `nq` points q [nq][p] (p = epg_num_params); used by the parity tests against
  * the fp64 oracle.  lp_out[nq], grad_out[nq][p]. */

@@ -26,3 +26,10 @@ def make_site(model, n, D, J, seed):
 def oracle_density(model, site):
     return dens.TiltedDensity(model, site['X'], site['y'], site['mu'], site['Omega'],
                               j_ind=site['j_ind'], J=site['J'])
+
+
+def bf16_round(x):
+    """round-to-nearest-even fp32 -> bf16 -> fp64 (what the tensor-core path stores)"""
+    u = np.asarray(x, dtype=np.float32).view(np.uint32).astype(np.uint64)
+    u = ((u + 0x7FFF + ((u >> 16) & 1)) >> 16) << 16
+    return u.astype(np.uint32).view(np.float32).astype(np.float64)

@@ -20,7 +20,7 @@ import synth
 pytestmark = pytest.mark.gpu
 
 
-def make_ctx(model, sites):
+def make_ctx(model, sites, use_tc=None):
     from epstan import _lib
     K = len(sites)
     d = sites[0]['d']
@@ -36,6 +36,8 @@ def make_ctx(model, sites):
                      [s['J'] for s in sites] if multi else None)
     ctx.upload(_lib.CAVQ, np.asfortranarray(np.stack([s['Omega'] for s in sites], axis=2)))
     ctx.upload(_lib.CAVM, np.asfortranarray(np.stack([s['mu'] for s in sites], axis=1)))
+    if use_tc is not None:
+        ctx.set_option('use_tc', use_tc)
     return ctx
 
 
@@ -43,7 +45,7 @@ def make_ctx(model, sites):
 @pytest.mark.parametrize('J,n,D', [(1, 37, 3), (1, 700, 19), (4, 90, 5), (3, 1300, 49)])
 def test_logdensity_parity(model, J, n, D):
     sites = [synth.make_site(model, n, D, J, seed=11), synth.make_site(model, n + 13, D, J, seed=12)]
-    ctx = make_ctx(model, sites)
+    ctx = make_ctx(model, sites, use_tc=0)          # the fp32 SIMT pass
     rng = np.random.RandomState(1)
     for k, site in enumerate(sites):
         td = synth.oracle_density(model, site)
@@ -54,6 +56,27 @@ def test_logdensity_parity(model, J, n, D):
         # fp32 contractions over n rows: a few 1e-6 relative per term
         assert np.max(np.abs(lp - olp) / np.maximum(1.0, np.abs(olp))) < 5e-5
         assert np.max(np.abs(grad - ograd)) < 2e-4 * max(1.0, np.max(np.abs(ograd)))
+    ctx.close()
+
+
+@pytest.mark.parametrize('model', dens.MODELS)
+@pytest.mark.parametrize('n,D', [(37, 3), (128, 8), (700, 19), (5000, 49), (1300, 63)])
+def test_logdensity_parity_tensor_core(model, n, D):
+    """tcgen05/TMA likelihood pass: X is stored in bf16 (a data quantisation, the
+    coefficients stay fp32-accurate through the hi/lo split), so the check is
+    against the fp64 oracle evaluated on the SAME bf16-rounded design matrix.
+    The gradient carries bf16 rounding of the residuals E (~2^-9 relative)."""
+    sites = [synth.make_site(model, n, D, 1, seed=31), synth.make_site(model, n + 77, D, 1, seed=32)]
+    ctx = make_ctx(model, sites, use_tc=1)
+    rng = np.random.RandomState(2)
+    for k, site in enumerate(sites):
+        site_q = dict(site, X=synth.bf16_round(site['X']))
+        td = synth.oracle_density(model, site_q)
+        q = 0.4 * rng.standard_normal((21, td.p))       # > 16: exercises batching
+        lp, grad = ctx.logdensity(k, q)
+        olp, ograd = td.lp_grad(q)
+        assert np.max(np.abs(lp - olp) / np.maximum(1.0, np.abs(olp))) < 5e-5
+        assert np.max(np.abs(grad - ograd)) < 6e-3 * max(1.0, np.max(np.abs(ograd)))
     ctx.close()
 
 
