@@ -27,14 +27,17 @@ constexpr int KW = 64;               // padded input columns (bf16) == one 128-b
 constexpr int NCH = 16;              // chains padded (N of both GEMMs)
 constexpr int NST = 8;               // X tile stages (TMA runs this far ahead)
 constexpr int NF = 4;                // F accumulator buffers in TMEM (GEMM1 runs this far ahead of the epilogue)
-constexpr int NE = 4;                // E operand buffers in smem (epilogue runs this far ahead of GEMM2)
+constexpr int NE = NST;              // E operand buffers in smem, one per X stage: a stage's E buffer is free
+                                     // exactly when its X tile is (GEMM2 of the previous user done), which the TMA
+                                     // producer has already waited for -> no separate "E free" barrier
 constexpr int TILE_BYTES = TILE_M * KW * 2;          // 16384
 constexpr int NB1 = 2 * NCH;         // GEMM1 N: columns [0,16) = hi parts, [16,32) = lo parts of the coefficients
 constexpr int B_BYTES = NB1 * KW * 2;                // 4096  (coefficient operand, hi | lo)
 constexpr int E_BYTES = NCH * TILE_M * 2;            // 4096  (one E buffer)
 constexpr int TMEM_COLS = 256;                       // F buffers [0, NF*32), G [NF*32, NF*32+16)
-constexpr int NBAR = 2 * NST + NF + 2 * NE + 1;
-constexpr int NTHREADS = 320;        // warps 0-7: epilogue (two halves x four TMEM lane quarters), 8: TMA, 9: MMA
+constexpr int NBAR = 2 * NST + NF + NE + 1;
+constexpr int NTHREADS = 352;        // warps 0-7: epilogue (two halves x four TMEM lane quarters), 8: GEMM1 issue,
+                                     // 9: GEMM2 issue (+ TMEM alloc), 10: TMA producer
 __host__ __device__ constexpr int chain_col(int c) { return (c & 1) * (NCH / 2) + (c >> 1); }
 
 struct Smem {            // offsets relative to a 1024-byte aligned base
@@ -62,6 +65,11 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t par) {
     const uint32_t a = smem_u32(bar);
     uint32_t done = 0;
+    asm volatile(                       // fast path: the phase has usually completed already
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(done) : "r"(a), "r"(par) : "memory");
     for (uint32_t spin = 0; !done; ++spin) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
@@ -155,10 +163,10 @@ __device__ __forceinline__ int interleave_off32(int n, int k) {
 }
 
 struct Bars {
-    uint64_t* full; uint64_t* empty; uint64_t* fready; uint64_t* eready; uint64_t* efree; uint64_t* gready;
+    uint64_t* full; uint64_t* empty; uint64_t* fready; uint64_t* eready; uint64_t* gready;
     __device__ explicit Bars(unsigned char* base) {
         uint64_t* b = reinterpret_cast<uint64_t*>(base + Smem::BAR);
-        full = b; empty = b + NST; fready = b + 2 * NST; eready = fready + NF; efree = eready + NE; gready = efree + NE;
+        full = b; empty = b + NST; fready = b + 2 * NST; eready = fready + NF; gready = eready + NE;
     }
 };
 
@@ -169,7 +177,7 @@ __device__ inline uint32_t setup(unsigned char* base) {
     if (tid == 0) {
         for (int i = 0; i < NST; ++i) { mbar_init(B.full + i, 1); mbar_init(B.empty + i, 1); }
         for (int i = 0; i < NF; ++i) mbar_init(B.fready + i, 1);
-        for (int i = 0; i < NE; ++i) { mbar_init(B.eready + i, 256); mbar_init(B.efree + i, 1); }
+        for (int i = 0; i < NE; ++i) mbar_init(B.eready + i, 256);
         mbar_init(B.gready, 1);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
@@ -222,32 +230,25 @@ __device__ inline void pass(unsigned char* base, uint32_t tmem_base, const CUten
     constexpr uint32_t IDESC1 = make_idesc(128, NB1, 0);
     constexpr uint32_t IDESC2 = make_idesc(64, NCH, 1);
 
-    if (warp == 8) {
-        // ===== TMA producer + GEMM1 issuer (warp runs converged; one elected lane issues) =====
-        const uint64_t bm_d = make_desc(smem_u32(base + Smem::BM), 512, 128, 0);
-        int next_tma = 0;
-        // issue every pending TMA load whose stage is free; block only when `must` names a tile GEMM1 needs now
-        auto tma_pump = [&](int upto, int must) {
-            while (next_tma < n_tiles && next_tma <= upto) {
-                const uint32_t gt = t0 + next_tma, slot = gt % NST, use = gt / NST;
-                if (use > 0) {
-                    if (next_tma <= must) mbar_wait(B.empty + slot, (use - 1) & 1);
-                    else if (!mbar_test(B.empty + slot, (use - 1) & 1)) break;
-                }
-                if (elect_one()) {
-                    mbar_expect_tx(B.full + slot, TILE_BYTES);
-                    tma_load_2d(base + Smem::X + slot * TILE_BYTES, tmap, B.full + slot, 0,
-                                (int)(row_begin + (int64_t)next_tma * TILE_M));
-                }
-                __syncwarp();
-                ++next_tma;
-            }
-        };
+    if (warp == 10) {
+        // ===== TMA producer (warp runs converged; one elected lane issues) =====
         for (int t = 0; t < n_tiles; ++t) {
-            tma_pump(t + NST - 1, t);
+            const uint32_t gt = t0 + t, slot = gt % NST, use = gt / NST;
+            if (use > 0) mbar_wait(B.empty + slot, (use - 1) & 1);     // GEMM2 of the previous user is done
+            if (elect_one()) {
+                mbar_expect_tx(B.full + slot, TILE_BYTES);
+                tma_load_2d(base + Smem::X + slot * TILE_BYTES, tmap, B.full + slot, 0,
+                            (int)(row_begin + (int64_t)t * TILE_M));
+            }
+            __syncwarp();
+        }
+    } else if (warp == 8) {
+        // ===== GEMM1 issuer (warp runs converged; one elected lane issues) =====
+        const uint64_t bm_d = make_desc(smem_u32(base + Smem::BM), 512, 128, 0);
+        for (int t = 0; t < n_tiles; ++t) {
             const uint32_t gt = t0 + t, slot = gt % NST, fb = gt % NF;
             // F buffer fb was last read by epilogue(gt - NF)
-            if (gt >= NF && t >= NF) mbar_wait(B.eready + (gt - NF) % NE, ((gt - NF) / NE) & 1);
+            if (t >= NF) mbar_wait(B.eready + (gt - NF) % NE, ((gt - NF) / NE) & 1);
             mbar_wait(B.full + slot, (gt / NST) & 1);
             tc_fence_after();
             const uint64_t xa_d = make_desc(xs + slot * TILE_BYTES, 16, 1024, 2);
@@ -279,7 +280,6 @@ __device__ inline void pass(unsigned char* base, uint32_t tmem_base, const CUten
                     umma(tmem_base + NF * NB1, xa_d + (uint64_t)(ks * 128), ea_d + (uint64_t)(ks * 32), IDESC2,
                          ks > 0 ? 1u : acc0);
                 umma_commit(B.empty + slot);
-                umma_commit(B.efree + eb_i);
             }
             __syncwarp();
             PROF_T(m3);
@@ -324,8 +324,7 @@ __device__ inline void pass(unsigned char* base, uint32_t tmem_base, const CUten
                 ev[c] = __float2bfloat16(keep * e);
             }
             PROF_T(p3);
-            if (gt >= NE) mbar_wait(B.efree + ebi, (gt / NE - 1) & 1);     // E buffer consumed by GEMM2(gt-NE)
-            PROF_T(p4);
+            PROF_T(p4);                       // (E buffer ebi is free: see NE)
             unsigned char* eb = base + Smem::E + ebi * E_BYTES;
 #pragma unroll
             for (int c = 0; c < NCPH; ++c)

@@ -201,15 +201,19 @@ struct SamplerArgs {
     int k0;
     // shared-memory plan
     int R, resident, slices, NC, combos;
-    int use_tc, hot_nvec, omega_smem;
+    int use_tc, hot_nvec, hot_levels, omega_smem;     // hot_levels: tree-stack levels kept in shared memory
     size_t off_E, off_B, off_G, off_gphi, off_lp, off_cs, off_hot, off_omega, smem_total;
 };
 
 __device__ __forceinline__ float* cvec(const SamplerArgs& a, int chain_global, int v) {
-    if (v < a.hot_nvec) {
+    const bool hot = v < a.hot_nvec;
+    const bool hot_stack = v >= V_STACK && v < V_STACK + 4 * a.hot_levels;
+    if (hot || hot_stack) {
         extern __shared__ __align__(1024) unsigned char smem_dyn[];
         const int c_local = chain_global - (a.k0 + (int)blockIdx.x) * a.C;
-        return reinterpret_cast<float*>(smem_dyn + a.off_hot) + ((size_t)c_local * a.hot_nvec + v) * a.P;
+        const int per_chain = a.hot_nvec + 4 * a.hot_levels;
+        const int slot = hot ? v : a.hot_nvec + (v - V_STACK);
+        return reinterpret_cast<float*>(smem_dyn + a.off_hot) + ((size_t)c_local * per_chain + slot) * a.P;
     }
     return a.chain_mem + ((size_t)chain_global * NVEC + v) * a.P;
 }
@@ -533,8 +537,20 @@ struct ChainCtx {
     const float* omega;   // [d*d] fp32 cavity precision
     const float* muf;     // [d] fp32 cavity mean
     ChainStack* stk;      // shared memory
-    __device__ float* v(int which) const { return cvec(a, cg, which); }
+    float* hot;           // this chain's block of shared-memory vectors (hot vectors, then hot stack levels)
+    float* cold;          // this chain's vectors in global memory
+    __device__ __forceinline__ float* v(int which) const {
+        if (which < a.hot_nvec) return hot + which * a.P;
+        if (which >= V_STACK && which < V_STACK + 4 * a.hot_levels) return hot + (a.hot_nvec + which - V_STACK) * a.P;
+        return cold + (size_t)which * a.P;
+    }
 };
+__device__ __forceinline__ ChainCtx make_chain_ctx(const SamplerArgs& a, int cg, int p, int d, int J, int D, int lane,
+                                                   uint2 key, const float* om, const float* muf, ChainStack* stk) {
+    float* hot = cvec(a, cg, 0);             // slot 0 of the chain's shared block (when hot_nvec > 0)
+    float* cold = a.chain_mem + (size_t)cg * NVEC * a.P;
+    return ChainCtx{a, cg, p, d, J, D, lane, key, om, muf, stk, hot, cold};
+}
 
 __device__ __forceinline__ void vcopy(const ChainCtx& x, int dst, int src) {
     float* D_ = x.v(dst); const float* S_ = x.v(src);
@@ -983,8 +999,8 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) k_nuts(const SamplerArgs a, c
         const long long tk0 = clock64();
         // ---- per-chain state machines ----
         for (int c = warp; worker && c < C; c += NWARP) {
-            ChainCtx x{a, k_local * C + c, p, d, J, D, lane, make_uint2(site_seed, (uint32_t)c),
-                       om, muf, cstk + c};
+            ChainCtx x = make_chain_ctx(a, k_local * C + c, p, d, J, D, lane, make_uint2(site_seed, (uint32_t)c),
+                                        om, muf, cstk + c);
             ChainS s = cs[c];                  // private copy: every lane runs the same scalar code
             const int before = s.phase;
             chain_step(x, s, lp_lik[c], c, k_local);
@@ -1117,7 +1133,7 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) k_logdensity(const SamplerArg
         likelihood_pass<CP>(a, smem, k_local, k_local, nq, J, row_begin, n_rows, grows, lp_lik);
     }
     for (int c = warp; worker && c < nq; c += NWARP) {
-        ChainCtx x{a, k_local * a.C + c, p, d, J, D, lane, make_uint2(0u, 0u), om, muf, nullptr};
+        ChainCtx x = make_chain_ctx(a, k_local * a.C + c, p, d, J, D, lane, make_uint2(0u, 0u), om, muf, nullptr);
         const double V = finish_gradient(x, lp_lik[c]);
         const float* g = x.v(V_G);
         if (lane == 0) lp_out[c] = -V;
@@ -1142,11 +1158,20 @@ bool plan_smem(SamplerArgs& a, int CP, int64_t max_rows, int d) {
     const size_t per_vec = sizeof(float) * (size_t)a.C * a.P;          // one hot vector of every chain
     // tail regions shared by both variants: [omega][hot vectors]
     auto place_tail = [&](size_t o) -> size_t {
-        a.omega_smem = 0; a.hot_nvec = 0; a.off_omega = a.off_hot = 0;
+        a.omega_smem = 0; a.hot_nvec = 0; a.hot_levels = 0; a.off_omega = a.off_hot = 0;
         if (o + sz_om <= budget && sz_om <= 48 * 1024) { a.omega_smem = 1; a.off_omega = o; o += sz_om; }
         int nv = per_vec ? (int)((budget - o) / per_vec) : 0;
-        if (nv > V_NHOT) nv = V_NHOT;
-        if (nv > 0) { a.hot_nvec = nv; a.off_hot = o; o += al16((size_t)nv * per_vec); }
+        int lv = 0;
+        if (nv > V_NHOT) {                      // room left: keep the lowest tree-stack levels on chip too
+            lv = (nv - V_NHOT) / 4;
+            if (lv > 4) lv = 4;
+            nv = V_NHOT;
+        }
+        a.hot_levels = 0;
+        if (nv > 0) {
+            a.hot_nvec = nv; a.hot_levels = lv; a.off_hot = o;
+            o += al16((size_t)(nv + 4 * lv) * per_vec);
+        }
         return o;
     };
     if (a.use_tc) {
