@@ -219,9 +219,10 @@ __device__ long long g_prof2[8];
 // lp partial sums per warp in `lpw` ([8 warps][NCH/2] doubles; warp w covers the
 // columns of half w>>2).  All NTHREADS threads must call it; the caller follows
 // with a __syncthreads.  NCPH = columns each epilogue half really processes.
-template <int NCPH>
+template <int NCPH, class Prologue>
 __device__ inline void pass(unsigned char* base, uint32_t tmem_base, const CUtensorMap* tmap, State& st,
-                            int64_t row_begin, int n_rows, int ksteps, const float* __restrict__ yglob, double* lpw) {
+                            int64_t row_begin, int n_rows, int ksteps, const float* __restrict__ yglob, double* lpw,
+                            Prologue&& prologue) {
     Bars B(base);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int n_tiles = (n_rows + TILE_M - 1) / TILE_M;
@@ -293,6 +294,7 @@ __device__ inline void pass(unsigned char* base, uint32_t tmem_base, const CUten
         const int half = warp >> 2;                   // columns [half*8, half*8+8)
         const int r = q * 32 + lane;                  // row within the tile
         const int col0 = half * (NCH / 2);
+        prologue();                                   // independent work that hides the pipeline fill
         float lpacc[NCPH];
 #pragma unroll
         for (int c = 0; c < NCPH; ++c) lpacc[c] = 0.0f;

@@ -202,7 +202,7 @@ struct SamplerArgs {
     // shared-memory plan
     int R, resident, slices, NC, combos;
     int use_tc, hot_nvec, hot_levels, omega_smem;     // hot_levels: tree-stack levels kept in shared memory
-    size_t off_E, off_B, off_G, off_gphi, off_lp, off_cs, off_hot, off_omega, smem_total;
+    size_t off_E, off_B, off_G, off_gphi, off_cavc, off_lp, off_cs, off_hot, off_omega, smem_total;
 };
 
 __device__ __forceinline__ float* cvec(const SamplerArgs& a, int chain_global, int v) {
@@ -238,13 +238,34 @@ __device__ __forceinline__ float logit_terms(float f, float yv, float& e) {
 
 #include "epg_lik_tc.cuh"
 
+// Cavity term of every chain, c = Omega (phi - mu), by the whole CTA (one (chain,row)
+// dot product per thread) into shared memory; consumed by finish_gradient.
+__device__ __forceinline__ void cavity_term(const SamplerArgs& a, unsigned char* smem, const float* om, const float* muf,
+                                            int k_local, int nchains, int nthr_workers) {
+    float* cavc = reinterpret_cast<float*>(smem + a.off_cavc);
+    const int d = a.d;
+    for (int e = threadIdx.x; e < nchains * d; e += nthr_workers) {
+        const int c = e / d, i = e - c * d;
+        const float* q = cvec(a, k_local * a.C + c, V_Q);
+        float acc0 = 0.0f, acc1 = 0.0f;
+        int j = 0;
+        for (; j + 1 < d; j += 2) {
+            acc0 = fmaf(om[i + (size_t)j * d], q[j] - muf[j], acc0);
+            acc1 = fmaf(om[i + (size_t)(j + 1) * d], q[j + 1] - muf[j + 1], acc1);
+        }
+        if (j < d) acc0 = fmaf(om[i + (size_t)j * d], q[j] - muf[j], acc0);
+        cavc[e] = acc0 + acc1;
+    }
+}
+
 // ---------------------------------------------------------------------------
 // Likelihood pass for all chains of one site: fills V_GL (likelihood part of
 // grad log p wrt every sampled parameter) and lp_out[c] (likelihood log-density).
 // ---------------------------------------------------------------------------
 template <int CP>
 __device__ void likelihood_pass(const SamplerArgs& a, unsigned char* smem, int site, int k_local, int nchains,
-                                int J, int64_t row_begin, int n_rows, const int* grows, double* lp_out) {
+                                int J, int64_t row_begin, int n_rows, const int* grows, double* lp_out,
+                                const float* om, const float* muf) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int S = a.S, D = a.D, d = a.d, model = a.model;
     float* Xs = reinterpret_cast<float*>(smem);
@@ -260,6 +281,7 @@ __device__ void likelihood_pass(const SamplerArgs& a, unsigned char* smem, int s
     const int ib = (model == EPG_M4B) ? 2 + D : 1;                  // start of log sigma_b (m3b/m4b)
 
     for (int e = tid; e < CP * d; e += NTHR) gphi[e] = 0.0f;
+    cavity_term(a, smem, om, muf, k_local, nchains, NTHR);
     float lpacc[CP];
 #pragma unroll
     for (int c = 0; c < CP; ++c) lpacc[c] = 0.0f;
@@ -445,7 +467,7 @@ __device__ void likelihood_pass(const SamplerArgs& a, unsigned char* smem, int s
 // ---------------------------------------------------------------------------
 __device__ void likelihood_pass_tc(const SamplerArgs& a, unsigned char* smem, unsigned char* tcb, uint32_t tmem_base,
                                    const CUtensorMap* tmap, tc::State& st, int k_local, int nchains,
-                                   int64_t row_begin, int n_rows, double* lp_out) {
+                                   int64_t row_begin, int n_rows, double* lp_out, const float* om, const float* muf) {
     const int tid = threadIdx.x;
     const bool worker = tid < NTHR;                  // warps 8, 9 only drive TMA / MMA inside the pass
     const int D = a.D, d = a.d, model = a.model;
@@ -456,7 +478,6 @@ __device__ void likelihood_pass_tc(const SamplerArgs& a, unsigned char* smem, un
     const int ib = (model == EPG_M4B) ? 2 + D : 1;
     PROF_T(q0);
     if (worker) {
-        for (int e = tid; e < tc::NCH * d; e += NTHR) gphi[e] = 0.0f;
         // coefficient operands B = B_hi + B_lo (bf16 each), K-major interleaved layout
         for (int e = tid; e < tc::NCH * tc::KW; e += NTHR) {
             const int c = e / tc::KW, col = e - c * tc::KW;
@@ -478,13 +499,17 @@ __device__ void likelihood_pass_tc(const SamplerArgs& a, unsigned char* smem, un
     __syncthreads();
     PROF_T(q1);
     const int ksteps = (D + 1 + 15) / 16;           // 16 input columns per tcgen05.mma
-    if (nchains <= 4) tc::pass<2>(tcb, tmem_base, tmap, st, row_begin, n_rows, ksteps, a.y, lpw);
-    else if (nchains <= 8) tc::pass<4>(tcb, tmem_base, tmap, st, row_begin, n_rows, ksteps, a.y, lpw);
-    else tc::pass<8>(tcb, tmem_base, tmap, st, row_begin, n_rows, ksteps, a.y, lpw);
+    // the cavity term is independent of the pass: the epilogue warps compute it while the
+    // first tiles are in flight
+    auto prologue = [&]() { cavity_term(a, smem, om, muf, k_local, nchains, NTHR); };
+    if (nchains <= 4) tc::pass<2>(tcb, tmem_base, tmap, st, row_begin, n_rows, ksteps, a.y, lpw, prologue);
+    else if (nchains <= 8) tc::pass<4>(tcb, tmem_base, tmap, st, row_begin, n_rows, ksteps, a.y, lpw, prologue);
+    else tc::pass<8>(tcb, tmem_base, tmap, st, row_begin, n_rows, ksteps, a.y, lpw, prologue);
     PROF_T(q2);
     __syncthreads();
     PROF_T(q3);
     if (worker) {
+        // chain rule (single group: every slot of the likelihood gradient gets exactly one term)
         const float* gout = reinterpret_cast<const float*>(tcb + tc::Smem::GOUT);
         for (int e = tid; e < tc::NCH * tc::KW; e += NTHR) {
             const int c = e / tc::KW, col = e - c * tc::KW;
@@ -495,16 +520,16 @@ __device__ void likelihood_pass_tc(const SamplerArgs& a, unsigned char* smem, un
             if (col == D) {
                 const float sa = __expf(q[ia]);
                 gl[d] = sa * gsum;
-                gphi[c * d + ia] += sa * q[d] * gsum;
-                if (model == EPG_M4B) gphi[c * d + 0] += gsum;
+                gl[ia] = sa * q[d] * gsum;
+                if (model == EPG_M4B) gl[0] = gsum;
             } else if (model == EPG_M1B) {
-                gphi[c * d + 1 + col] += gsum;
+                gl[1 + col] = gsum;
             } else {
                 const float sb = __expf(q[ib + col]);
                 const float etb = q[d + 1 + col];
                 gl[d + 1 + col] = sb * gsum;
-                gphi[c * d + ib + col] += sb * etb * gsum;
-                if (model == EPG_M4B) gphi[c * d + 2 + col] += gsum;
+                gl[ib + col] = sb * etb * gsum;
+                if (model == EPG_M4B) gl[2 + col] = gsum;
             }
         }
         if (tid < nchains) {
@@ -516,14 +541,10 @@ __device__ void likelihood_pass_tc(const SamplerArgs& a, unsigned char* smem, un
         }
     }
     __syncthreads();
-    if (worker)
-        for (int e = tid; e < tc::NCH * d; e += NTHR) {
-            const int c = e / d, i = e - c * d;
-            if (c < nchains) cvec(a, chain0 + c, V_GL)[i] = gphi[e];
-        }
-    __syncthreads();
     PROF_T(q4);
+#ifdef EPG_TC_PROFILE
     if (threadIdx.x == 0) { PROF2_ADD(2, q0, q1); PROF2_ADD(3, q1, q2); PROF2_ADD(4, q2, q3); PROF2_ADD(5, q3, q4); PROF2_ADD(6, 0, 1); }
+#endif
 }
 
 // ---------------------------------------------------------------------------
@@ -537,6 +558,7 @@ struct ChainCtx {
     const float* omega;   // [d*d] fp32 cavity precision
     const float* muf;     // [d] fp32 cavity mean
     ChainStack* stk;      // shared memory
+    const float* cavc;    // [d] cavity term Omega (phi - mu) of this chain (shared memory)
     float* hot;           // this chain's block of shared-memory vectors (hot vectors, then hot stack levels)
     float* cold;          // this chain's vectors in global memory
     __device__ __forceinline__ float* v(int which) const {
@@ -549,12 +571,16 @@ __device__ __forceinline__ ChainCtx make_chain_ctx(const SamplerArgs& a, int cg,
                                                    uint2 key, const float* om, const float* muf, ChainStack* stk) {
     float* hot = cvec(a, cg, 0);             // slot 0 of the chain's shared block (when hot_nvec > 0)
     float* cold = a.chain_mem + (size_t)cg * NVEC * a.P;
-    return ChainCtx{a, cg, p, d, J, D, lane, key, om, muf, stk, hot, cold};
+    extern __shared__ __align__(1024) unsigned char smem_dyn2[];
+    const int c_local = cg - (a.k0 + (int)blockIdx.x) * a.C;
+    const float* cavc = reinterpret_cast<const float*>(smem_dyn2 + a.off_cavc) + (size_t)c_local * d;
+    return ChainCtx{a, cg, p, d, J, D, lane, key, om, muf, stk, cavc, hot, cold};
 }
 
 __device__ __forceinline__ void vcopy(const ChainCtx& x, int dst, int src) {
-    float* D_ = x.v(dst); const float* S_ = x.v(src);
-    for (int i = x.lane; i < x.p; i += 32) D_[i] = S_[i];
+    float4* D_ = reinterpret_cast<float4*>(x.v(dst));
+    const float4* S_ = reinterpret_cast<const float4*>(x.v(src));
+    for (int i = x.lane; 4 * i < x.p; i += 32) D_[i] = S_[i];       // vectors are padded to P (multiple of 32)
 }
 
 // kinetic energy 0.5 p' M^-1 p
@@ -574,8 +600,7 @@ __device__ double finish_gradient(const ChainCtx& x, double lp_lik) {
     const int d = x.d;
     float quad = 0.0f, sq = 0.0f;
     for (int i = x.lane; i < d; i += 32) {
-        float ci = 0.0f;
-        for (int j = 0; j < d; ++j) ci = fmaf(x.omega[i + (size_t)j * d], q[j] - x.muf[j], ci);
+        const float ci = x.cavc[i];               // Omega (phi - mu), computed by cavity_term()
         quad += ci * (q[i] - x.muf[i]);
         g[i] = ci - gl[i];
     }
@@ -1015,8 +1040,8 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) k_nuts(const SamplerArgs a, c
         __syncthreads();
         if (n_active <= 0) break;
         const long long tk1 = clock64();
-        if (a.use_tc) likelihood_pass_tc(a, smem, tcb, tmem_base, &tmap, tcst, k_local, C, row_begin, n_rows, lp_lik);
-        else likelihood_pass<CP>(a, smem, k_local, k_local, C, J, row_begin, n_rows, grows, lp_lik);
+        if (a.use_tc) likelihood_pass_tc(a, smem, tcb, tmem_base, &tmap, tcst, k_local, C, row_begin, n_rows, lp_lik, om, muf);
+        else likelihood_pass<CP>(a, smem, k_local, k_local, C, J, row_begin, n_rows, grows, lp_lik, om, muf);
         clk_chain += tk1 - tk0;
         clk_lik += clock64() - tk1;
         ++n_ticks;
@@ -1126,11 +1151,11 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) k_logdensity(const SamplerArg
     __threadfence_block();
     __syncthreads();
     if (a.use_tc) {
-        likelihood_pass_tc(a, smem, tcb, tmem_base, &tmap, tcst, k_local, nq, row_begin, n_rows, lp_lik);
+        likelihood_pass_tc(a, smem, tcb, tmem_base, &tmap, tcst, k_local, nq, row_begin, n_rows, lp_lik, om, muf);
         // second evaluation: exercises the pipeline state carried across ticks
-        likelihood_pass_tc(a, smem, tcb, tmem_base, &tmap, tcst, k_local, nq, row_begin, n_rows, lp_lik);
+        likelihood_pass_tc(a, smem, tcb, tmem_base, &tmap, tcst, k_local, nq, row_begin, n_rows, lp_lik, om, muf);
     } else {
-        likelihood_pass<CP>(a, smem, k_local, k_local, nq, J, row_begin, n_rows, grows, lp_lik);
+        likelihood_pass<CP>(a, smem, k_local, k_local, nq, J, row_begin, n_rows, grows, lp_lik, om, muf);
     }
     for (int c = warp; worker && c < nq; c += NWARP) {
         ChainCtx x = make_chain_ctx(a, k_local * a.C + c, p, d, J, D, lane, make_uint2(0u, 0u), om, muf, nullptr);
@@ -1179,6 +1204,7 @@ bool plan_smem(SamplerArgs& a, int CP, int64_t max_rows, int d) {
         a.off_E = a.off_B = a.off_G = 0;
         a.R = 0; a.resident = 0; a.slices = 1; a.NC = 1; a.combos = 1;
         a.off_gphi = o; o += al16(sizeof(float) * (size_t)tc::NCH * d);
+        a.off_cavc = o; o += al16(sizeof(float) * (size_t)tc::NCH * d);
         a.off_lp = o; o += al16(sizeof(double) * (size_t)NWARP * tc::NCH);
         a.off_cs = o; o += sz_cs;
         if (o > budget) return false;
@@ -1199,7 +1225,7 @@ bool plan_smem(SamplerArgs& a, int CP, int64_t max_rows, int d) {
         const size_t szG = al16(sizeof(float) * (size_t)a.slices * CP * S);
         const size_t szg = al16(sizeof(float) * (size_t)CP * d);
         const size_t szl = al16(sizeof(double) * (size_t)NWARP * CP);
-        const size_t rest = szE + szB + szG + szg + szl + sz_cs;
+        const size_t rest = szE + szB + szG + 2 * szg + szl + sz_cs;
         const size_t xres = al16(sizeof(float) * (size_t)max_rows * S);
         const size_t xstream = al16(2 * sizeof(float) * (size_t)a.R * S);
         size_t xbytes;
@@ -1212,6 +1238,7 @@ bool plan_smem(SamplerArgs& a, int CP, int64_t max_rows, int d) {
             a.off_B = o; o += szB;
             a.off_G = o; o += szG;
             a.off_gphi = o; o += szg;
+            a.off_cavc = o; o += szg;
             a.off_lp = o; o += szl;
             a.off_cs = o; o += sz_cs;
             a.smem_total = place_tail(o);
