@@ -20,6 +20,7 @@ nuts.py        fp64 NumPy restatement of Stan 2.17's adaptive diag_e NUTS
                (published algorithm; PyStan 2.17.0.0 is an un-vendored
                dependency of the reference and is not installed here).
                "parity unpinned": statistical checks only.
-nuts_c/        the same sampler in plain C (gcc, OpenMP) used as the timed CPU
-               baseline of bench.py.
+fakes.py       deterministic Gaussian sampler double shared by make_golden.py and
+               the tests.
+make_golden.py generates tests/golden/*.npz from the unmodified reference.
 """
