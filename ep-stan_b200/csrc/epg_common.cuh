@@ -10,6 +10,7 @@
 struct Grp {
     int tid, n;
     __device__ __forceinline__ Grp() : tid(threadIdx.x), n(blockDim.x) {}
+    __device__ __forceinline__ Grp(int t, int nn) : tid(t), n(nn) {}     // e.g. one warp of the CTA
     __device__ __forceinline__ void sync() const {
         if (n <= EPG_WARP) __syncwarp(); else __syncthreads();
     }

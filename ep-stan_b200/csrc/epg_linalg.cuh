@@ -16,9 +16,20 @@ __device__ __forceinline__ void pk_advance(int& i, int& k, int step, int d) {
     while (i >= d && k < d) { i = i - d + k + 1; ++k; }
 }
 
+// Optional lookup table of the (row, col) of every packed-lower element, built once per
+// kernel in shared memory: tri[e] = (row << 8) | col.  Replaces the index walk in the
+// O(d^2)-per-column loops.
+__device__ inline void build_tri_table(const Grp& g, unsigned short* tri, int d) {
+    for (int j = g.tid; j < d; j += g.n) {
+        const int cj = pk_col(j, d);
+        for (int i = j; i < d; ++i) tri[cj + i] = (unsigned short)((i << 8) | j);
+    }
+    g.sync();
+}
+
 // In-place Cholesky  A = L L'.  Returns false (uniformly) when a pivot is not
 // strictly positive or not finite (LAPACK dpotrf info>0).  Ends with a barrier.
-__device__ inline bool chol_packed(const Grp& g, double* A, int d) {
+__device__ inline bool chol_packed(const Grp& g, double* A, int d, const unsigned short* tri = nullptr) {
     for (int j = 0; j < d; ++j) {
         g.sync();
         const double ajj = A[pk(j, j, d)];
@@ -31,11 +42,18 @@ __device__ inline bool chol_packed(const Grp& g, double* A, int d) {
         // trailing update A(i,k) -= L(i,j) L(k,j), j<k<=i : the packed tail
         const int base = pk(j + 1, j + 1, d);           // valid also when j+1==d (== size)
         const int m = pk_size(d) - base;
-        int i = j + 1, k = j + 1;
-        pk_advance(i, k, g.tid, d);
-        for (int e = g.tid; e < m; e += g.n) {
-            A[base + e] -= A[cj + i] * A[cj + k];
-            pk_advance(i, k, g.n, d);
+        if (tri) {
+            for (int e = g.tid; e < m; e += g.n) {
+                const unsigned ik = tri[base + e];
+                A[base + e] -= A[cj + (ik >> 8)] * A[cj + (ik & 255u)];
+            }
+        } else {
+            int i = j + 1, k = j + 1;
+            pk_advance(i, k, g.tid, d);
+            for (int e = g.tid; e < m; e += g.n) {
+                A[base + e] -= A[cj + i] * A[cj + k];
+                pk_advance(i, k, g.n, d);
+            }
         }
     }
     g.sync();
@@ -60,7 +78,7 @@ __device__ inline void bwd_solve_packed(const Grp& g, const double* L, double* b
     for (int j = d - 1; j >= 0; --j) {
         g.sync();
         const double xj = b[j] / L[pk(j, j, d)];
-        for (int k = g.tid; k < j; k += g.n) b[k] -= L[pk(j, k, d)] * xj;
+        for (int k = g.tid; k < j; k += g.n) b[k] -= L[pk(j, k, d)] * xj;   // (row j of L)
     }
     g.sync();
     for (int j = g.tid; j < d; j += g.n) b[j] /= L[pk(j, j, d)];
@@ -82,7 +100,8 @@ __device__ inline void trtri_packed(const Grp& g, double* L, double* col, int d)
             else {
                 // new(i) = -xjj * sum_{k=j+1..i} X(i,k) * Lold(k,j)
                 acc = 0.0;
-                for (int k = j + 1; k <= i; ++k) acc += L[pk(i, k, d)] * col[k];
+                int idx = pk(i, j + 1, d);                 // (i, k) -> (i, k+1): + d - k - 1
+                for (int k = j + 1; k <= i; ++k) { acc += L[idx] * col[k]; idx += d - k - 1; }
                 acc *= -xjj;
             }
             L[cj + i] = acc;
@@ -94,11 +113,13 @@ __device__ inline void trtri_packed(const Grp& g, double* L, double* col, int d)
 // out = scale * X' X for lower-triangular X (packed): the full symmetric d x d
 // result, written column-major to `out` (global or shared).  Both triangles are
 // written: this is dpotri followed by copy_triu_to_tril.
-__device__ inline void lauum_full(const Grp& g, const double* X, int d, double scale, double* out) {
+__device__ inline void lauum_full(const Grp& g, const double* X, int d, double scale, double* out,
+                                  const unsigned short* tri = nullptr) {
     const int m = pk_size(d);
     int i = 0, j = 0;
     pk_advance(i, j, g.tid, d);
     for (int e = g.tid; e < m; e += g.n) {
+        if (tri) { const unsigned ij = tri[e]; i = (int)(ij >> 8); j = (int)(ij & 255u); }
         // (i,j), i >= j : sum_{k>=i} X(k,i) X(k,j)
         const double* ci = X + pk_col(i, d);
         const double* cj = X + pk_col(j, d);
@@ -107,7 +128,7 @@ __device__ inline void lauum_full(const Grp& g, const double* X, int d, double s
         acc *= scale;
         out[i + j * d] = acc;
         out[j + i * d] = acc;
-        pk_advance(i, j, g.n, d);
+        if (!tri) pk_advance(i, j, g.n, d);
     }
 }
 

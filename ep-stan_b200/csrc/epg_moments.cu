@@ -21,7 +21,7 @@ namespace {
 
 struct MomSmem {
     int da, dpad, T, nb_rows, NB, nslices;
-    size_t off_gram, off_chunk, off_vec, off_part, total;
+    size_t off_gram, off_chunk, off_vec, off_part, off_tri, total;
 };
 
 __host__ __device__ inline MomSmem mom_layout(int d, int nthr) {
@@ -41,6 +41,8 @@ __host__ __device__ inline MomSmem mom_layout(int d, int nthr) {
     L.off_chunk = o; o += sizeof(double) * (size_t)L.T * L.dpad;
     L.off_part = o;  // per-slice partial tiles (only when nslices > 1)
     if (L.nslices > 1) o += sizeof(double) * (size_t)L.nslices * L.NB * 16;
+    L.off_tri = o;   // (row,col) lookup of the packed scatter matrix
+    if (d <= 128) o += (sizeof(unsigned short) * (size_t)pk_size(d) + 15) & ~(size_t)15;   // (large d: index walk)
     L.total = o;
     return L;
 }
@@ -65,6 +67,7 @@ __global__ void k_moments(const double* __restrict__ draws, int n, int d, int k0
     double* vec = reinterpret_cast<double*>(smem_raw + L.off_vec);
     double* xs = reinterpret_cast<double*>(smem_raw + L.off_chunk);    // [T][dpad]
     double* part = reinterpret_cast<double*>(smem_raw + L.off_part);
+    unsigned short* tri = d <= 128 ? reinterpret_cast<unsigned short*>(smem_raw + L.off_tri) : nullptr;
     double* shift = vec;            // d
     double* mt = vec + d;           // d
     double* sol = vec + 2 * d;      // d
@@ -75,6 +78,7 @@ __global__ void k_moments(const double* __restrict__ draws, int n, int d, int k0
     const double* x = draws + (size_t)k * d * n;
 
     for (int e = g.tid; e < pk_size(da); e += g.n) gram[e] = 0.0;
+    if (tri) build_tri_table(g, tri, d);
     // provisional mean of the first chunk
     {
         const int t0n = n < T ? n : T;
@@ -96,12 +100,38 @@ __global__ void k_moments(const double* __restrict__ draws, int n, int d, int k0
 #pragma unroll
     for (int q = 0; q < 16; ++q) acc[q] = 0.0;
 
+    // software pipeline: the draws of chunk c+1 are fetched into registers while chunk c is reduced
+    constexpr int PF = 8;                       // elements per thread per chunk that are prefetched
+    double pre[PF];
+    const bool pf_ok = (T * d + g.n - 1) / g.n <= PF;
+    auto fetch = [&](int c0) {
+        const int tn = (n - c0) < T ? (n - c0) : T;
+#pragma unroll
+        for (int u = 0; u < PF; ++u) {
+            const int idx = g.tid + u * g.n;
+            const int t = idx % T, i = idx / T;
+            pre[u] = (idx < T * d && t < tn) ? x[(size_t)i * n + c0 + t] : 0.0;
+        }
+    };
+    if (pf_ok) fetch(0);
     for (int c0 = 0; c0 < n; c0 += T) {
         const int tn = (n - c0) < T ? (n - c0) : T;
         // load + shift + transpose: xs[t][0]=1, xs[t][1+i] = x_i - a_i, zero padding
-        for (int idx = g.tid; idx < T * d; idx += g.n) {
-            const int t = idx % T, i = idx / T;
-            xs[t * dpad + 1 + i] = (t < tn) ? x[(size_t)i * n + c0 + t] - shift[i] : 0.0;
+        if (pf_ok) {
+#pragma unroll
+            for (int u = 0; u < PF; ++u) {
+                const int idx = g.tid + u * g.n;
+                if (idx < T * d) {
+                    const int t = idx % T, i = idx / T;
+                    xs[t * dpad + 1 + i] = (t < tn) ? pre[u] - shift[i] : 0.0;
+                }
+            }
+            if (c0 + T < n) fetch(c0 + T);
+        } else {
+            for (int idx = g.tid; idx < T * d; idx += g.n) {
+                const int t = idx % T, i = idx / T;
+                xs[t * dpad + 1 + i] = (t < tn) ? x[(size_t)i * n + c0 + t] - shift[i] : 0.0;
+            }
         }
         for (int idx = g.tid; idx < T * (dpad - d); idx += g.n) {
             const int t = idx % T, i = idx / T;       // i = 0 -> the constant, else padding
@@ -187,28 +217,63 @@ __global__ void k_moments(const double* __restrict__ draws, int n, int d, int k0
     g.sync();
     {
         const double post = (MODE == EPG_PREC_OLSE) ? inv_n : 1.0;
-        int i = 0, j = 0;
-        pk_advance(i, j, g.tid, d);
-        for (int e = g.tid; e < pk_size(d); e += g.n) {
-            A[e] = (A[e] - gram[1 + i] * gram[1 + j] * inv_n) * post;
-            pk_advance(i, j, g.n, d);
+        if (tri) {
+            for (int e = g.tid; e < pk_size(d); e += g.n) {
+                const unsigned ij = tri[e];
+                A[e] = (A[e] - gram[1 + (ij >> 8)] * gram[1 + (ij & 255u)] * inv_n) * post;
+            }
+        } else {
+            int i = 0, j = 0;
+            pk_advance(i, j, g.tid, d);
+            for (int e = g.tid; e < pk_size(d); e += g.n) {
+                A[e] = (A[e] - gram[1 + i] * gram[1 + j] * inv_n) * post;
+                pk_advance(i, j, g.n, d);
+            }
         }
     }
     g.sync();
 
     double* outQ = dQi + (size_t)k * d * d;
     double* outr = dri + (size_t)k * d;
-    bool good = chol_packed(g, A, d);
-    if (good) {
-        if (MODE == EPG_PREC_SAMPLE) {
-            fwd_solve_packed(g, A, sol, d);
-            bwd_solve_packed(g, A, sol, d);
+    // Small matrices: the column-sequential factorisation / inversion is done by ONE warp with
+    // warp-level barriers (a CTA-wide barrier per column step costs more than the step);
+    // the other warps wait.  Large matrices use the whole CTA.
+    const double kf = (MODE == EPG_PREC_SAMPLE) ? (double)(n - d - 2) : 1.0;
+    // (measured at K=1024, d=50: the one-warp variant is ~30 % slower than the CTA-wide one -> disabled)
+    const bool one_warp = false;
+    bool good;
+    if (one_warp) {
+        __shared__ int s_good;
+        if (g.tid < EPG_WARP) {
+            const Grp w(g.tid, EPG_WARP);
+            bool ok_w = chol_packed(w, A, d, tri);
+            if (ok_w) {
+                if (MODE == EPG_PREC_SAMPLE) {
+                    fwd_solve_packed(w, A, sol, d);
+                    bwd_solve_packed(w, A, sol, d);
+                }
+                trtri_packed(w, A, col, d);
+                lauum_full(w, A, d, kf, outQ, tri);
+            }
+            if (g.tid == 0) s_good = ok_w ? 1 : 0;
         }
-        trtri_packed(g, A, col, d);
-        const double kf = (MODE == EPG_PREC_SAMPLE) ? (double)(n - d - 2) : 1.0;
-        lauum_full(g, A, d, kf, outQ);
         __threadfence_block();
         g.sync();
+        good = s_good != 0;
+    } else {
+        good = chol_packed(g, A, d, tri);
+        if (good) {
+            if (MODE == EPG_PREC_SAMPLE) {
+                fwd_solve_packed(g, A, sol, d);
+                bwd_solve_packed(g, A, sol, d);
+            }
+            trtri_packed(g, A, col, d);
+            lauum_full(g, A, d, kf, outQ, tri);
+        }
+        __threadfence_block();
+        g.sync();
+    }
+    if (good) {
         if (MODE == EPG_PREC_SAMPLE) {
             double bad = 0.0;
             for (int e = g.tid; e < d * d; e += g.n) {

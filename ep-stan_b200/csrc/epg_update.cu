@@ -13,6 +13,7 @@ namespace {
 __host__ __device__ inline size_t linalg_smem(int d) {
     return sizeof(double) * ((size_t)pk_size(d) + 5 * (size_t)d + 48);
 }
+// (measured: one warp per matrix with warp-level barriers is slower than these CTA sizes at d = 20..50)
 inline int linalg_threads(int d) { return d <= 16 ? 32 : (d <= 32 ? 64 : (d <= 64 ? 128 : (d <= 128 ? 256 : 512))); }
 
 // ------------------------------------------------------------------ cavity
