@@ -191,3 +191,26 @@ def test_full_ep_vs_oracle_ep(model):
     assert kl < 0.25, kl
     sd = np.sqrt(np.diag(oSs[-1]))
     assert np.all(np.abs(ms[-1] - oms[-1]) < 0.6 * sd)
+
+
+def test_config5_shape_large_d_many_chains():
+    """config-5-like shape on the SIMT pass (D+1 > 64, 32 chains): density parity at d=200
+    and a short adaptive run that must produce finite, well-mixed draws."""
+    model, n, D, C = 'm1b', 1500, 199, 32
+    site = synth.make_site(model, n, D, 1, seed=41)
+    site['Omega'] = site['Omega'] + 4.0 * np.eye(D + 1)
+    ctx = make_ctx(model, [site, site])
+    td = synth.oracle_density(model, site)
+    rng = np.random.RandomState(3)
+    q = 0.1 * rng.standard_normal((5, td.p))
+    lp, grad = ctx.logdensity(0, q)
+    olp, ograd = td.lp_grad(q)
+    assert np.max(np.abs(lp - olp) / np.maximum(1.0, np.abs(olp))) < 5e-5
+    assert np.max(np.abs(grad - ograd)) < 5e-4 * max(1.0, np.max(np.abs(ograd)))
+    msteps, mrhat, nleap, secs = ctx.tilted_sample([5, 6], C, 120, 60)
+    dr = ctx.get_draws(C * 60)
+    assert dr.shape == (2, D + 1, C * 60) and np.all(np.isfinite(dr))
+    assert np.all(msteps > 0) and np.all(mrhat < 1.5) and np.all(nleap > 0)
+    oks, n_ok = ctx.moments(C * 60, 'sample')
+    assert oks.all()
+    ctx.close()
