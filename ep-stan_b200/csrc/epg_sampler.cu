@@ -614,6 +614,48 @@ __device__ double finish_gradient(const ChainCtx& x, double lp_lik) {
     return -(lp_lik + prior);
 }
 
+// Fused consume step of a tree leaf: gradient/potential from the likelihood pass, second half
+// of the leapfrog, kinetic energy and the leaf's node vectors (rho = p, p_sharp = M^-1 p,
+// proposal = this point) in ONE pass over the parameter vector and ONE round of warp reductions.
+__device__ void leaf_fused(const ChainCtx& x, double lp_lik, float eps_signed, double& Vnew, double& kin) {
+    const float* q = x.v(V_Q);
+    const float* gl = x.v(V_GL);
+    const float* minv = x.v(V_MINV);
+    float* g = x.v(V_G); float* p = x.v(V_P);
+    float* crho = x.v(V_CRHO); float* cpsl = x.v(V_CPSL);
+    float* qp_ = x.v(V_QPROP); float* gp_ = x.v(V_GPROP);
+    const int d = x.d;
+    float prior2 = 0.0f, kin2 = 0.0f;                 // (phi-mu)'Omega(phi-mu) + |latents|^2 ;  p'M^-1 p
+    for (int i = x.lane; i < x.p; i += 32) {
+        const float qi = q[i];
+        float gi;
+        if (i < d) {
+            const float ci = x.cavc[i];
+            prior2 = fmaf(ci, qi - x.muf[i], prior2);
+            gi = ci - gl[i];
+        } else {
+            prior2 = fmaf(qi, qi, prior2);
+            gi = qi - gl[i];
+        }
+        const float pi = p[i] - 0.5f * eps_signed * gi;
+        const float mp = minv[i] * pi;
+        kin2 = fmaf(mp, pi, kin2);
+        g[i] = gi; p[i] = pi;
+        crho[i] = pi; cpsl[i] = mp;
+        qp_[i] = qi; gp_[i] = gi;
+    }
+    // two reductions interleaved
+    double a = (double)prior2, b = (double)kin2;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
+    }
+    __syncwarp();
+    Vnew = -(lp_lik - 0.5 * a);
+    kin = 0.5 * b;
+}
+
 __device__ void sample_momentum(const ChainCtx& x, ChainS& s) {
     const float* minv = x.v(V_MINV);
     float* p = x.v(V_P);
@@ -825,7 +867,10 @@ __device__ void chain_step(const ChainCtx& x, ChainS& s, double lp_lik, int c_lo
         return;
     }
     // ---- consume ----
-    const double Vnew = finish_gradient(x, lp_lik);
+    double Vnew, kin_leaf = 0.0;
+    const bool tree_leaf = s.phase == PH_TREE_WAIT;
+    if (tree_leaf) leaf_fused(x, lp_lik, s.sign * s.eps, Vnew, kin_leaf);
+    else Vnew = finish_gradient(x, lp_lik);
     if (s.phase == PH_SS_WAIT) {
         leapfrog_end(x, s.eps);
         double h = Vnew + kinetic(x, x.v(V_P));
@@ -854,10 +899,8 @@ __device__ void chain_step(const ChainCtx& x, ChainS& s, double lp_lik, int c_lo
         return;
     }
     // ---- PH_TREE_WAIT: a new leaf of the current subtree ----
-    const float es = s.sign * s.eps;
-    leapfrog_end(x, es);
     s.V = Vnew;
-    double h = Vnew + kinetic(x, x.v(V_P));
+    double h = Vnew + kin_leaf;
     if (isnan(h)) h = INFINITY;
     s.n_leap_tr += 1;
     const double dH = s.H0 - h;
@@ -867,18 +910,8 @@ __device__ void chain_step(const ChainCtx& x, ChainS& s, double lp_lik, int c_lo
         end_transition(x, s, c_local, site_draw);
         return;
     }
-    // leaf node: rho = p, p_sharp(left) = M^-1 p, proposal = this point
-    {
-        const float* p = x.v(V_P); const float* minv = x.v(V_MINV);
-        float* crho = x.v(V_CRHO); float* cpsl = x.v(V_CPSL);
-        const float* q = x.v(V_Q); const float* g = x.v(V_G);
-        float* qp_ = x.v(V_QPROP); float* gp_ = x.v(V_GPROP);
-        for (int i = x.lane; i < x.p; i += 32) {
-            crho[i] = p[i]; cpsl[i] = minv[i] * p[i];
-            qp_[i] = q[i]; gp_[i] = g[i];
-        }
-        __syncwarp();
-    }
+    // (leaf node vectors -- rho = p, p_sharp(left) = M^-1 p, proposal = this point -- were
+    //  written by leaf_fused)
     s.cur_lsw = dH;
     s.Vprop = Vnew;
     int l = 0;
@@ -916,8 +949,13 @@ __device__ void chain_step(const ChainCtx& x, ChainS& s, double lp_lik, int c_lo
     }
     if (l < s.depth) {
         const int base = V_STACK + 4 * l;
-        vcopy(x, base + 0, V_CPSL); vcopy(x, base + 1, V_CRHO);
-        vcopy(x, base + 2, V_QPROP); vcopy(x, base + 3, V_GPROP);
+        {
+            float4* d0 = reinterpret_cast<float4*>(x.v(base + 0)); const float4* s0 = reinterpret_cast<const float4*>(x.v(V_CPSL));
+            float4* d1 = reinterpret_cast<float4*>(x.v(base + 1)); const float4* s1 = reinterpret_cast<const float4*>(x.v(V_CRHO));
+            float4* d2 = reinterpret_cast<float4*>(x.v(base + 2)); const float4* s2 = reinterpret_cast<const float4*>(x.v(V_QPROP));
+            float4* d3 = reinterpret_cast<float4*>(x.v(base + 3)); const float4* s3 = reinterpret_cast<const float4*>(x.v(V_GPROP));
+            for (int i = x.lane; 4 * i < x.p; i += 32) { d0[i] = s0[i]; d1[i] = s1[i]; d2[i] = s2[i]; d3[i] = s3[i]; }
+        }
         if (x.lane == 0) { x.stk->lsw[l] = s.cur_lsw; x.stk->V[l] = s.Vprop; }
         __syncwarp();
         s.nleaf += 1;
