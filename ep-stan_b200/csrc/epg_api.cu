@@ -74,6 +74,8 @@ int epg_create(epg_ctx** out, int device, void* stream, int own_stream) {
     if (cudaSetDevice(device) != cudaSuccess) return -1;
     epg_ctx* c = new epg_ctx();
     c->device = device;
+    if (cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) c->num_sms = 148;
+    { int l2 = 0; if (cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, device) == cudaSuccess && l2 > 0) c->l2_bytes = (size_t)l2; }
     if (!own_stream) { c->stream = (cudaStream_t)stream; c->own_stream = false; }
     else {
         if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return -1; }

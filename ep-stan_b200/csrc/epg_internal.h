@@ -9,6 +9,8 @@ struct epg_site_data;      // sampler-side site data (epg_sampler.cu)
 
 struct epg_ctx {
     int device = 0;
+    int num_sms = 148;
+    size_t l2_bytes = 126u << 20;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     std::string err;

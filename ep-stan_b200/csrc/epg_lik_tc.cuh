@@ -25,8 +25,10 @@ namespace tc {
 constexpr int TILE_M = 128;          // rows per tile
 constexpr int KW = 64;               // padded input columns (bf16) == one 128-byte swizzle row
 constexpr int NCH = 16;              // chains padded (N of both GEMMs)
-constexpr int NST = 8;               // X tile stages (TMA runs this far ahead)
-constexpr int NF = 4;                // F accumulator buffers in TMEM (GEMM1 runs this far ahead of the epilogue)
+constexpr int NST = 8;               // max X tile stages (TMA runs this far ahead); the launch picks nst in NF..NST
+                                     // (State::nst): 8 when one site owns the CTA, fewer in the two-site kernel
+constexpr int NF = 4;                // F accumulator buffers in TMEM (GEMM1 runs this far ahead of the epilogue);
+                                     // NF <= nst, so that a barrier is never more than one phase ahead of a waiter
 constexpr int NE = NST;              // E operand buffers in smem, one per X stage: a stage's E buffer is free
                                      // exactly when its X tile is (GEMM2 of the previous user done), which the TMA
                                      // producer has already waited for -> no separate "E free" barrier
@@ -41,13 +43,13 @@ constexpr int NTHREADS = 352;        // warps 0-7: epilogue (two halves x four T
 __host__ __device__ constexpr int chain_col(int c) { return (c & 1) * (NCH / 2) + (c >> 1); }
 
 struct Smem {            // offsets relative to a 1024-byte aligned base
-    static constexpr int X = 0;
-    static constexpr int BM = NST * TILE_BYTES;      // coefficient operand [32 x 64] (hi rows | lo rows)
-    static constexpr int E = BM + B_BYTES;
-    static constexpr int BAR = E + NE * E_BYTES;
+    static constexpr int BM = 0;                     // coefficient operand [32 x 64] (hi rows | lo rows)
+    static constexpr int GOUT = BM + B_BYTES;        // float [NCH][KW]
+    static constexpr int BAR = GOUT + NCH * KW * 4;
     static constexpr int TMEM_PTR = BAR + NBAR * 8;
-    static constexpr int GOUT = TMEM_PTR + 16;       // float [NCH][KW]
-    static constexpr int TOTAL = GOUT + NCH * KW * 4;
+    static constexpr int E = (TMEM_PTR + 16 + 1023) & ~1023;          // nst E buffers
+    __host__ __device__ static constexpr int X(int nst) { return E + nst * E_BYTES; }     // nst X tiles (1024-aligned)
+    __host__ __device__ static constexpr int total(int nst) { return X(nst) + nst * TILE_BYTES; }
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -171,7 +173,7 @@ struct Bars {
 };
 
 // one-time setup by the whole CTA (called once per kernel): barriers + TMEM
-__device__ inline uint32_t setup(unsigned char* base) {
+__device__ inline uint32_t setup(unsigned char* base, int nst) {
     Bars B(base);
     const int tid = threadIdx.x;
     if (tid == 0) {
@@ -181,7 +183,7 @@ __device__ inline uint32_t setup(unsigned char* base) {
         mbar_init(B.gready, 1);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
-    for (int e = tid; e < NE * E_BYTES / 4; e += blockDim.x) reinterpret_cast<uint32_t*>(base + Smem::E)[e] = 0u;
+    for (int e = tid; e < nst * E_BYTES / 4; e += blockDim.x) reinterpret_cast<uint32_t*>(base + Smem::E)[e] = 0u;
     if ((tid >> 5) == 9) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n"
                      ::"r"(smem_u32(base + Smem::TMEM_PTR)), "n"(TMEM_COLS) : "memory");
@@ -199,7 +201,16 @@ __device__ inline void teardown(uint32_t tmem_base) {
 }
 
 // Running counters of the pipelines (they persist over the ticks of a kernel).
-struct State { uint32_t tiles = 0; uint32_t ticks = 0; };
+struct State {
+    uint32_t tiles = 0, ticks = 0;       // tiles: global index of the next tile (F buffer = tiles % NF)
+    uint32_t nst = NST;                  // X/E stages in use (NF <= nst <= NST)
+    uint32_t slot = 0, use = 0;          // tiles % nst, tiles / nst, kept incrementally (nst need not be a power of two)
+    __device__ void set_stages(int n) { nst = (uint32_t)(n < NF ? NF : (n > NST ? NST : n)); }
+};
+// (slot, use) of the tile after / NF tiles before the given one
+__device__ __forceinline__ void ring_next(uint32_t nst, uint32_t& slot, uint32_t& use) {
+    if (++slot == nst) { slot = 0; ++use; }
+}
 #ifdef EPG_TC_PROFILE
 __device__ long long g_prof[8];
 #define PROF_T(var) const long long var = clock64()
@@ -227,18 +238,20 @@ __device__ inline void pass(unsigned char* base, uint32_t tmem_base, const CUten
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int n_tiles = (n_rows + TILE_M - 1) / TILE_M;
     const uint32_t t0 = st.tiles;                  // global index of this tick's first tile
-    const uint32_t xs = smem_u32(base + Smem::X);
+    const uint32_t nst = st.nst;
+    const int x_off = Smem::X((int)nst);
+    const uint32_t xs = smem_u32(base + x_off);
     constexpr uint32_t IDESC1 = make_idesc(128, NB1, 0);
     constexpr uint32_t IDESC2 = make_idesc(64, NCH, 1);
 
     if (warp == 10) {
         // ===== TMA producer (warp runs converged; one elected lane issues) =====
-        for (int t = 0; t < n_tiles; ++t) {
-            const uint32_t gt = t0 + t, slot = gt % NST, use = gt / NST;
+        uint32_t slot = st.slot, use = st.use;
+        for (int t = 0; t < n_tiles; ++t, ring_next(nst, slot, use)) {
             if (use > 0) mbar_wait(B.empty + slot, (use - 1) & 1);     // GEMM2 of the previous user is done
             if (elect_one()) {
                 mbar_expect_tx(B.full + slot, TILE_BYTES);
-                tma_load_2d(base + Smem::X + slot * TILE_BYTES, tmap, B.full + slot, 0,
+                tma_load_2d(base + x_off + slot * TILE_BYTES, tmap, B.full + slot, 0,
                             (int)(row_begin + (int64_t)t * TILE_M));
             }
             __syncwarp();
@@ -246,11 +259,15 @@ __device__ inline void pass(unsigned char* base, uint32_t tmem_base, const CUten
     } else if (warp == 8) {
         // ===== GEMM1 issuer (warp runs converged; one elected lane issues) =====
         const uint64_t bm_d = make_desc(smem_u32(base + Smem::BM), 512, 128, 0);
-        for (int t = 0; t < n_tiles; ++t) {
-            const uint32_t gt = t0 + t, slot = gt % NST, fb = gt % NF;
-            // F buffer fb was last read by epilogue(gt - NF)
-            if (t >= NF) mbar_wait(B.eready + (gt - NF) % NE, ((gt - NF) / NE) & 1);
-            mbar_wait(B.full + slot, (gt / NST) & 1);
+        uint32_t slot = st.slot, use = st.use;
+        for (int t = 0; t < n_tiles; ++t, ring_next(nst, slot, use)) {
+            const uint32_t gt = t0 + t, fb = gt % NF;
+            // F buffer fb was last read by epilogue(gt - NF), whose E buffer sits NF stages back in the ring
+            if (t >= NF) {
+                const bool wrap = slot < (uint32_t)NF;
+                mbar_wait(B.eready + (wrap ? slot + nst - NF : slot - NF), (wrap ? use - 1 : use) & 1);
+            }
+            mbar_wait(B.full + slot, use & 1);
             tc_fence_after();
             const uint64_t xa_d = make_desc(xs + slot * TILE_BYTES, 16, 1024, 2);
             const uint32_t dF = tmem_base + fb * NB1;
@@ -265,10 +282,11 @@ __device__ inline void pass(unsigned char* base, uint32_t tmem_base, const CUten
     } else if (warp == 9) {
         // ===== GEMM2 issuer (warp runs converged; one elected lane issues) =====
         const uint32_t eb = smem_u32(base + Smem::E);
-        for (int t = 0; t < n_tiles; ++t) {
-            const uint32_t gt = t0 + t, slot = gt % NST, eb_i = gt % NE;
+        uint32_t slot = st.slot, use = st.use;
+        for (int t = 0; t < n_tiles; ++t, ring_next(nst, slot, use)) {
+            const uint32_t eb_i = slot;
             PROF_T(m0);
-            mbar_wait(B.eready + eb_i, (gt / NE) & 1);
+            mbar_wait(B.eready + eb_i, use & 1);
             tc_fence_after();
             PROF_T(m1);
             const uint64_t xa_d = make_desc(xs + slot * TILE_BYTES, 1024, 1024, 2);
@@ -299,8 +317,9 @@ __device__ inline void pass(unsigned char* base, uint32_t tmem_base, const CUten
 #pragma unroll
         for (int c = 0; c < NCPH; ++c) lpacc[c] = 0.0f;
         float y_next = (r < n_rows) ? yglob[row_begin + r] : 0.0f;
-        for (int t = 0; t < n_tiles; ++t) {
-            const uint32_t gt = t0 + t, fb = gt % NF, ebi = gt % NE;
+        uint32_t ebi = st.slot, euse = st.use;
+        for (int t = 0; t < n_tiles; ++t, ring_next(nst, ebi, euse)) {
+            const uint32_t gt = t0 + t, fb = gt % NF;
             const int row = t * TILE_M + r;
             const float keep = row < n_rows ? 1.0f : 0.0f;
             const float yv = y_next;
@@ -362,6 +381,11 @@ __device__ inline void pass(unsigned char* base, uint32_t tmem_base, const CUten
     }
     st.tiles += (uint32_t)n_tiles;
     st.ticks += 1;
+    {   // advance the ring position by n_tiles
+        const uint32_t adv = st.slot + (uint32_t)n_tiles;
+        st.use += adv / nst;
+        st.slot = adv % nst;
+    }
 }
 
 }  // namespace tc

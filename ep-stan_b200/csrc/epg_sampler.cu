@@ -51,6 +51,7 @@ struct epg_site_data {
     CUtensorMap tmap;                   // TMA descriptor of Xb: box 64 x 128 rows, 128-byte swizzle
     bool tc_ok = false;                 // tensor-core pass usable (single group, D+1 <= 64)
     int use_tc = 1;                     // option (epg_set_option "use_tc")
+    int pp_mode = 1;                    // option "pingpong": 0 never, 1 when sites > SMs, 2 always (tests)
     float* y = nullptr;                 // [N]
     int64_t* row0 = nullptr;            // [K+1]
     int* grp_ptr = nullptr;             // [K+1] offsets into grp_rows
@@ -201,21 +202,24 @@ struct SamplerArgs {
     int k0;
     // shared-memory plan
     int R, resident, slices, NC, combos;
-    int use_tc, hot_nvec, hot_levels, omega_smem;     // hot_levels: tree-stack levels kept in shared memory
+    int use_tc, tc_nst, pp, hot_nvec, hot_levels, omega_smem;     // tc_nst: X/E stages of the tensor-core pass     // hot_levels: tree-stack levels kept in shared memory
     size_t off_E, off_B, off_G, off_gphi, off_cavc, off_lp, off_cs, off_hot, off_omega, smem_total;
+    size_t site_stride;                // ping-pong kernel: distance between the two per-site blocks
 };
 
-__device__ __forceinline__ float* cvec(const SamplerArgs& a, int chain_global, int v) {
+// One site as a CTA sees it: its index and the base of its block of shared memory (the per-site offsets of
+// SamplerArgs are relative to `sm`; the ping-pong kernel keeps two such blocks).
+struct SiteView { unsigned char* sm; int k; };
+
+__device__ __forceinline__ float* cvec(const SamplerArgs& a, const SiteView& sv, int c_local, int v) {
     const bool hot = v < a.hot_nvec;
     const bool hot_stack = v >= V_STACK && v < V_STACK + 4 * a.hot_levels;
     if (hot || hot_stack) {
-        extern __shared__ __align__(1024) unsigned char smem_dyn[];
-        const int c_local = chain_global - (a.k0 + (int)blockIdx.x) * a.C;
         const int per_chain = a.hot_nvec + 4 * a.hot_levels;
         const int slot = hot ? v : a.hot_nvec + (v - V_STACK);
-        return reinterpret_cast<float*>(smem_dyn + a.off_hot) + ((size_t)c_local * per_chain + slot) * a.P;
+        return reinterpret_cast<float*>(sv.sm + a.off_hot) + ((size_t)c_local * per_chain + slot) * a.P;
     }
-    return a.chain_mem + ((size_t)chain_global * NVEC + v) * a.P;
+    return a.chain_mem + ((size_t)(sv.k * a.C + c_local) * NVEC + v) * a.P;
 }
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
@@ -246,7 +250,7 @@ __device__ __forceinline__ void cavity_term(const SamplerArgs& a, unsigned char*
     const int d = a.d;
     for (int e = threadIdx.x; e < nchains * d; e += nthr_workers) {
         const int c = e / d, i = e - c * d;
-        const float* q = cvec(a, k_local * a.C + c, V_Q);
+        const float* q = cvec(a, SiteView{smem, k_local}, c, V_Q);
         float acc0 = 0.0f, acc1 = 0.0f;
         int j = 0;
         for (; j + 1 < d; j += 2) {
@@ -301,7 +305,7 @@ __device__ void likelihood_pass(const SamplerArgs& a, unsigned char* smem, int s
             const int c = e / S, col = e - c * S;
             float v = 0.0f;
             if (c < nchains && col <= D) {
-                const float* q = cvec(a, chain0 + c, V_Q);
+                const float* q = cvec(a, SiteView{smem, k_local}, c, V_Q);
                 if (col == D) {
                     const float sa = __expf(q[ia]);
                     v = q[d + j] * sa + (model == EPG_M4B ? q[0] : 0.0f);
@@ -422,8 +426,8 @@ __device__ void likelihood_pass(const SamplerArgs& a, unsigned char* smem, int s
             if (c >= nchains || col > D) continue;
             float gsum = 0.0f;
             for (int sl = 0; sl < slices; ++sl) gsum += Gp[((size_t)sl * CP + c) * S + col];
-            const float* q = cvec(a, chain0 + c, V_Q);
-            float* gl = cvec(a, chain0 + c, V_GL);
+            const float* q = cvec(a, SiteView{smem, k_local}, c, V_Q);
+            float* gl = cvec(a, SiteView{smem, k_local}, c, V_GL);
             if (col == D) {
                 // s_j = sum_n e_n
                 const float sa = __expf(q[ia]);
@@ -456,7 +460,7 @@ __device__ void likelihood_pass(const SamplerArgs& a, unsigned char* smem, int s
     }
     for (int e = tid; e < CP * d; e += NTHR) {
         const int c = e / d, i = e - c * d;
-        if (c < nchains) cvec(a, chain0 + c, V_GL)[i] = gphi[e];
+        if (c < nchains) cvec(a, SiteView{smem, k_local}, c, V_GL)[i] = gphi[e];
     }
     __syncthreads();
 }
@@ -465,13 +469,15 @@ __device__ void likelihood_pass(const SamplerArgs& a, unsigned char* smem, int s
 // Tensor-core variant of the likelihood pass (single-group sites, D+1 <= 64,
 // <= 16 chains): see epg_lik_tc.cuh.  Same outputs as likelihood_pass.
 // ---------------------------------------------------------------------------
+// barrier over the tc::NTHREADS likelihood threads only (== the whole CTA except in the ping-pong kernel)
+__device__ __forceinline__ void lik_group_sync() { asm volatile("bar.sync 1, %0;\n" ::"n"(tc::NTHREADS) : "memory"); }
+
 __device__ void likelihood_pass_tc(const SamplerArgs& a, unsigned char* smem, unsigned char* tcb, uint32_t tmem_base,
                                    const CUtensorMap* tmap, tc::State& st, int k_local, int nchains,
                                    int64_t row_begin, int n_rows, double* lp_out, const float* om, const float* muf) {
     const int tid = threadIdx.x;
     const bool worker = tid < NTHR;                  // warps 8, 9 only drive TMA / MMA inside the pass
     const int D = a.D, d = a.d, model = a.model;
-    float* gphi = reinterpret_cast<float*>(smem + a.off_gphi);
     double* lpw = reinterpret_cast<double*>(smem + a.off_lp);       // [NWARP][8]
     const int chain0 = k_local * a.C;
     const int ia = (model == EPG_M4B) ? 1 : 0;
@@ -483,7 +489,7 @@ __device__ void likelihood_pass_tc(const SamplerArgs& a, unsigned char* smem, un
             const int c = e / tc::KW, col = e - c * tc::KW;
             float v = 0.0f;
             if (c < nchains && col <= D) {
-                const float* q = cvec(a, chain0 + c, V_Q);
+                const float* q = cvec(a, SiteView{smem, k_local}, c, V_Q);
                 if (col == D) v = q[d] * __expf(q[ia]) + (model == EPG_M4B ? q[0] : 0.0f);
                 else if (model == EPG_M1B) v = q[1 + col];
                 else v = q[d + 1 + col] * __expf(q[ib + col]) + (model == EPG_M4B ? q[2 + col] : 0.0f);
@@ -496,7 +502,7 @@ __device__ void likelihood_pass_tc(const SamplerArgs& a, unsigned char* smem, un
         }
         tc::fence_proxy_async();
     }
-    __syncthreads();
+    lik_group_sync();
     PROF_T(q1);
     const int ksteps = (D + 1 + 15) / 16;           // 16 input columns per tcgen05.mma
     // the cavity term is independent of the pass: the epilogue warps compute it while the
@@ -506,7 +512,7 @@ __device__ void likelihood_pass_tc(const SamplerArgs& a, unsigned char* smem, un
     else if (nchains <= 8) tc::pass<4>(tcb, tmem_base, tmap, st, row_begin, n_rows, ksteps, a.y, lpw, prologue);
     else tc::pass<8>(tcb, tmem_base, tmap, st, row_begin, n_rows, ksteps, a.y, lpw, prologue);
     PROF_T(q2);
-    __syncthreads();
+    lik_group_sync();
     PROF_T(q3);
     if (worker) {
         // chain rule (single group: every slot of the likelihood gradient gets exactly one term)
@@ -515,8 +521,8 @@ __device__ void likelihood_pass_tc(const SamplerArgs& a, unsigned char* smem, un
             const int c = e / tc::KW, col = e - c * tc::KW;
             if (c >= nchains || col > D) continue;
             const float gsum = gout[tc::chain_col(c) * tc::KW + col];
-            const float* q = cvec(a, chain0 + c, V_Q);
-            float* gl = cvec(a, chain0 + c, V_GL);
+            const float* q = cvec(a, SiteView{smem, k_local}, c, V_Q);
+            float* gl = cvec(a, SiteView{smem, k_local}, c, V_GL);
             if (col == D) {
                 const float sa = __expf(q[ia]);
                 gl[d] = sa * gsum;
@@ -540,7 +546,7 @@ __device__ void likelihood_pass_tc(const SamplerArgs& a, unsigned char* smem, un
             lp_out[tid] = sum;
         }
     }
-    __syncthreads();
+    lik_group_sync();
     PROF_T(q4);
 #ifdef EPG_TC_PROFILE
     if (threadIdx.x == 0) { PROF2_ADD(2, q0, q1); PROF2_ADD(3, q1, q2); PROF2_ADD(4, q2, q3); PROF2_ADD(5, q3, q4); PROF2_ADD(6, 0, 1); }
@@ -567,13 +573,13 @@ struct ChainCtx {
         return cold + (size_t)which * a.P;
     }
 };
-__device__ __forceinline__ ChainCtx make_chain_ctx(const SamplerArgs& a, int cg, int p, int d, int J, int D, int lane,
-                                                   uint2 key, const float* om, const float* muf, ChainStack* stk) {
-    float* hot = cvec(a, cg, 0);             // slot 0 of the chain's shared block (when hot_nvec > 0)
+__device__ __forceinline__ ChainCtx make_chain_ctx(const SamplerArgs& a, const SiteView& sv, int c_local, int p, int d,
+                                                   int J, int D, int lane, uint2 key, const float* om,
+                                                   const float* muf, ChainStack* stk) {
+    const int cg = sv.k * a.C + c_local;
+    float* hot = cvec(a, sv, c_local, 0);    // slot 0 of the chain's shared block (when hot_nvec > 0)
     float* cold = a.chain_mem + (size_t)cg * NVEC * a.P;
-    extern __shared__ __align__(1024) unsigned char smem_dyn2[];
-    const int c_local = cg - (a.k0 + (int)blockIdx.x) * a.C;
-    const float* cavc = reinterpret_cast<const float*>(smem_dyn2 + a.off_cavc) + (size_t)c_local * d;
+    const float* cavc = reinterpret_cast<const float*>(sv.sm + a.off_cavc) + (size_t)c_local * d;
     return ChainCtx{a, cg, p, d, J, D, lane, key, om, muf, stk, cavc, hot, cold};
 }
 
@@ -992,51 +998,21 @@ __device__ void chain_step(const ChainCtx& x, ChainS& s, double lp_lik, int c_lo
 }
 
 // ---------------------------------------------------------------------------
-// the persistent sampling kernel: one CTA per site
+// pieces shared by the sampling kernels
 // ---------------------------------------------------------------------------
-template <int CP>
-__global__ void __launch_bounds__(tc::NTHREADS, 1) k_nuts(const SamplerArgs a, const __grid_constant__ CUtensorMap tmap) {
-    extern __shared__ __align__(1024) unsigned char smem[];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int k_local = a.k0 + blockIdx.x;
-    const int C = a.C, d = a.d, D = a.D, S = a.S;
-    const int64_t row_begin = a.row0[k_local];
-    const int n_rows = (int)(a.row0[k_local + 1] - row_begin);
-    const int* grows = a.grp_rows + a.grp_ptr[k_local];
-    const int J = a.grp_ptr[k_local + 1] - a.grp_ptr[k_local] - 1;
-    const int p = model_np(a.model, D, J);
-    ChainS* cs = reinterpret_cast<ChainS*>(smem + a.off_cs);
-    ChainStack* cstk = reinterpret_cast<ChainStack*>(smem + a.off_cs + sizeof(ChainS) * 32);
-    __shared__ double lp_lik[32];
-    __shared__ int n_active;
-
-    // (the tensor-core variant runs with two extra warps, 8 = TMA and 9 = MMA issue,
-    //  which take part only in the barriers and in tc::pass)
-    const bool worker = tid < NTHR;
-    // cavity precision -> fp32 copy (read by every chain every tick)
-    float* om = a.omega_smem ? reinterpret_cast<float*>(smem + a.off_omega)
-                             : a.omega + (size_t)k_local * (d * d + d);
+// cavity precision / mean -> fp32 copies (read by every chain every tick); thread t of a group of nthr
+__device__ __forceinline__ void load_cavity(const SamplerArgs& a, int k, float* om, int t, int nthr) {
+    const int d = a.d;
+    const double* cq = a.cavQ + (size_t)k * d * d;
     float* muf = om + d * d;
-    const double* cq = a.cavQ + (size_t)k_local * d * d;
-    if (worker) {
-        for (int e = tid; e < d * d; e += NTHR) om[e] = (float)cq[e];
-        for (int i = tid; i < d; i += NTHR) muf[i] = (float)a.cavm[(size_t)k_local * d + i];
-    }
-    // resident design matrix
-    if (a.resident && !a.use_tc) {
-        const float4* src = reinterpret_cast<const float4*>(a.X + (size_t)row_begin * S);
-        float4* dst = reinterpret_cast<float4*>(smem);
-        for (int e = tid; e < n_rows * (S >> 2); e += NTHR) dst[e] = src[e];
-    }
-    // tensor-core pass: barriers + tensor memory
-    unsigned char* tcb = smem + ((1024u - (tc::smem_u32(smem) & 1023u)) & 1023u);
-    uint32_t tmem_base = 0;
-    tc::State tcst;
-    if (a.use_tc) tmem_base = tc::setup(tcb);
-    // chain state
-    for (int c = warp; worker && c < C; c += NWARP) {
+    for (int e = t; e < d * d; e += nthr) om[e] = (float)cq[e];
+    for (int i = t; i < d; i += nthr) muf[i] = (float)a.cavm[(size_t)k * d + i];
+}
+
+// initial state of the site's chains; warp w of a group of nw warps
+__device__ __forceinline__ void init_chains(const SamplerArgs& a, const SiteView& sv, ChainS* cs, int w, int nw, int lane) {
+    for (int c = w; c < a.C; c += nw) {
         ChainS& s = cs[c];
-        const int cg = k_local * C + c;
         if (lane == 0) {
             memset(&s, 0, sizeof(ChainS));
             s.phase = PH_START;
@@ -1048,10 +1024,134 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) k_nuts(const SamplerArgs a, c
         }
         const int vecs[] = {V_WMEAN, V_WM2, V_RS0, V_RQ0, V_RS1, V_RQ1};
         for (int i = lane; i < a.P; i += 32) {
-            cvec(a, cg, V_MINV)[i] = 1.0f;
-            for (int v = 0; v < 6; ++v) cvec(a, cg, vecs[v])[i] = 0.0f;
+            cvec(a, sv, c, V_MINV)[i] = 1.0f;
+            for (int v = 0; v < 6; ++v) cvec(a, sv, c, vecs[v])[i] = 0.0f;
         }
     }
+}
+
+// one chain phase of a site: every chain advances to its next gradient request; warp w of nw
+__device__ __forceinline__ void chain_phase(const SamplerArgs& a, const SiteView& sv, ChainS* cs, ChainStack* cstk,
+                                            const double* lp_lik, int* n_active, int p, int J, uint32_t site_seed,
+                                            const float* om, const float* muf, int w, int nw, int lane) {
+    for (int c = w; c < a.C; c += nw) {
+        ChainCtx x = make_chain_ctx(a, sv, c, p, a.d, J, a.D, lane, make_uint2(site_seed, (uint32_t)c), om, muf, cstk + c);
+        ChainS s = cs[c];                  // private copy: every lane runs the same scalar code
+        const int before = s.phase;
+        chain_step(x, s, lp_lik[c], c, sv.k);
+        __syncwarp();
+        if (lane == 0) {
+            cs[c] = s;
+            if ((s.phase == PH_DONE || s.phase == PH_DEAD) && !(before == PH_DONE || before == PH_DEAD))
+                atomicSub(n_active, 1);
+        }
+    }
+}
+
+// per-site analytics by one warp: mean step size, max split-Rhat, leapfrogs
+__device__ void site_analytics(const SamplerArgs& a, const SiteView& sv, const ChainS* cs, int p, int lane,
+                               double clk_chain, double clk_lik, double n_ticks) {
+    const int C = a.C;
+    const int per = a.iter - a.warmup;
+    const int hn = per / 2;
+    float worst = 0.0f;
+    if (hn >= 2 && C >= 1) {
+        for (int i = lane; i < p; i += 32) {
+            // split chains: 2C sequences of hn draws
+            float mean_all = 0.0f, W = 0.0f;
+            int m = 0;
+            for (int c = 0; c < C; ++c) {
+                if (cs[c].phase != PH_DONE) continue;
+                for (int h = 0; h < 2; ++h) {
+                    const float sm = cvec(a, sv, c, h ? V_RS1 : V_RS0)[i];
+                    const float sq = cvec(a, sv, c, h ? V_RQ1 : V_RQ0)[i];
+                    const float ref = cvec(a, sv, c, V_WMEAN)[i];
+                    const float mu = sm / hn;
+                    W += (sq - hn * mu * mu) / (hn - 1);
+                    mean_all += mu + ref;
+                    ++m;
+                }
+            }
+            if (m >= 2) {
+                mean_all /= m; W /= m;
+                float B = 0.0f;
+                for (int c = 0; c < C; ++c) {
+                    if (cs[c].phase != PH_DONE) continue;
+                    for (int h = 0; h < 2; ++h) {
+                        const float mu = cvec(a, sv, c, h ? V_RS1 : V_RS0)[i] / hn + cvec(a, sv, c, V_WMEAN)[i];
+                        B += (mu - mean_all) * (mu - mean_all);
+                    }
+                }
+                B = B * hn / (m - 1);
+                const float var_plus = (hn - 1.0f) / hn * W + B / hn;
+                const float rhat = W > 0.0f ? sqrtf(var_plus / W) : 1.0f;
+                worst = fmaxf(worst, rhat);
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) worst = fmaxf(worst, __shfl_xor_sync(0xffffffffu, worst, o));
+    if (lane == 0) {
+        double eps_mean = 0.0, nl = 0.0, nd = 0.0;
+        int ok = 0;
+        for (int c = 0; c < C; ++c) {
+            nl += (double)cs[c].n_leap_total;
+            nd += cs[c].n_div;
+            if (cs[c].phase == PH_DONE) { eps_mean += cs[c].eps_sum / (per > 0 ? per : 1); ++ok; }
+        }
+        double* o = a.out + (size_t)sv.k * 8;
+        o[4] = clk_chain; o[5] = clk_lik; o[6] = n_ticks; o[7] = 0.0;
+        o[0] = ok ? eps_mean / ok : NAN;
+        o[1] = (ok == C) ? (double)worst : NAN;
+        o[2] = nl;
+        o[3] = (ok == C) ? nd : -1.0;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// the persistent sampling kernel: one CTA per site
+// ---------------------------------------------------------------------------
+// USE_TC false: fp32 SIMT likelihood pass (NTHR threads); true: tensor-core pass (tc::NTHREADS threads)
+template <int CP, bool USE_TC>
+__global__ void __launch_bounds__(USE_TC ? tc::NTHREADS : NTHR, 1)
+k_nuts(const SamplerArgs a, const __grid_constant__ CUtensorMap tmap) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int k_local = a.k0 + blockIdx.x;
+    const int C = a.C, d = a.d, D = a.D, S = a.S;
+    const int64_t row_begin = a.row0[k_local];
+    const int n_rows = (int)(a.row0[k_local + 1] - row_begin);
+    const int* grows = a.grp_rows + a.grp_ptr[k_local];
+    const int J = a.grp_ptr[k_local + 1] - a.grp_ptr[k_local] - 1;
+    const int p = model_np(a.model, D, J);
+    const SiteView sv{smem, k_local};
+    ChainS* cs = reinterpret_cast<ChainS*>(smem + a.off_cs);
+    ChainStack* cstk = reinterpret_cast<ChainStack*>(smem + a.off_cs + sizeof(ChainS) * a.C);
+    __shared__ double lp_lik[32];
+    __shared__ int n_active;
+
+    // (the tensor-core variant runs with three extra warps, 8/9 = MMA issue and 10 = TMA,
+    //  which take part only in the barriers and in tc::pass)
+    const bool worker = tid < NTHR;
+    float* om = a.omega_smem ? reinterpret_cast<float*>(smem + a.off_omega)
+                             : a.omega + (size_t)k_local * (d * d + d);
+    float* muf = om + d * d;
+    if (worker) load_cavity(a, k_local, om, tid, NTHR);
+    // resident design matrix
+    if (!USE_TC && a.resident) {
+        const float4* src = reinterpret_cast<const float4*>(a.X + (size_t)row_begin * S);
+        float4* dst = reinterpret_cast<float4*>(smem);
+        for (int e = tid; e < n_rows * (S >> 2); e += NTHR) dst[e] = src[e];
+    }
+    // tensor-core pass: barriers + tensor memory
+    unsigned char* tcb = smem + ((1024u - (tc::smem_u32(smem) & 1023u)) & 1023u);
+    uint32_t tmem_base = 0;
+    tc::State tcst;
+    if constexpr (USE_TC) {
+        tcst.set_stages(a.tc_nst);
+        tmem_base = tc::setup(tcb, a.tc_nst);
+    }
+    if (worker) init_chains(a, sv, cs, warp, NWARP, lane);
     if (tid == 0) n_active = C;
     __threadfence_block();
     __syncthreads();
@@ -1060,92 +1160,124 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) k_nuts(const SamplerArgs a, c
     long long clk_chain = 0, clk_lik = 0, n_ticks = 0;
     for (;;) {
         const long long tk0 = clock64();
-        // ---- per-chain state machines ----
-        for (int c = warp; worker && c < C; c += NWARP) {
-            ChainCtx x = make_chain_ctx(a, k_local * C + c, p, d, J, D, lane, make_uint2(site_seed, (uint32_t)c),
-                                        om, muf, cstk + c);
-            ChainS s = cs[c];                  // private copy: every lane runs the same scalar code
-            const int before = s.phase;
-            chain_step(x, s, lp_lik[c], c, k_local);
-            __syncwarp();
-            if (lane == 0) {
-                cs[c] = s;
-                if ((s.phase == PH_DONE || s.phase == PH_DEAD) && !(before == PH_DONE || before == PH_DEAD))
-                    atomicSub(&n_active, 1);
-            }
-        }
+        if (worker) chain_phase(a, sv, cs, cstk, lp_lik, &n_active, p, J, site_seed, om, muf, warp, NWARP, lane);
         __threadfence_block();
         __syncthreads();
         if (n_active <= 0) break;
         const long long tk1 = clock64();
-        if (a.use_tc) likelihood_pass_tc(a, smem, tcb, tmem_base, &tmap, tcst, k_local, C, row_begin, n_rows, lp_lik, om, muf);
+        if constexpr (USE_TC) likelihood_pass_tc(a, smem, tcb, tmem_base, &tmap, tcst, k_local, C, row_begin, n_rows, lp_lik, om, muf);
         else likelihood_pass<CP>(a, smem, k_local, k_local, C, J, row_begin, n_rows, grows, lp_lik, om, muf);
         clk_chain += tk1 - tk0;
         clk_lik += clock64() - tk1;
         ++n_ticks;
     }
-    if (a.use_tc) tc::teardown(tmem_base);
-
-    // ---- per-site analytics: mean step size, max split-Rhat, leapfrogs ----
+    if constexpr (USE_TC) tc::teardown(tmem_base);
     __syncthreads();
-    if (warp == 0) {
-        const int per = a.iter - a.warmup;
-        const int hn = per / 2;
-        float worst = 0.0f;
-        if (hn >= 2 && C >= 1) {
-            for (int i = lane; i < p; i += 32) {
-                // split chains: 2C sequences of hn draws
-                float mean_all = 0.0f, W = 0.0f;
-                int m = 0;
-                for (int c = 0; c < C; ++c) {
-                    if (cs[c].phase != PH_DONE) continue;
-                    const int cg = k_local * C + c;
-                    for (int h = 0; h < 2; ++h) {
-                        const float sm = cvec(a, cg, h ? V_RS1 : V_RS0)[i];
-                        const float sq = cvec(a, cg, h ? V_RQ1 : V_RQ0)[i];
-                        const float ref = cvec(a, cg, V_WMEAN)[i];
-                        const float mu = sm / hn;
-                        W += (sq - hn * mu * mu) / (hn - 1);
-                        mean_all += mu + ref;
-                        ++m;
-                    }
-                }
-                if (m >= 2) {
-                    mean_all /= m; W /= m;
-                    float B = 0.0f;
-                    for (int c = 0; c < C; ++c) {
-                        if (cs[c].phase != PH_DONE) continue;
-                        const int cg = k_local * C + c;
-                        for (int h = 0; h < 2; ++h) {
-                            const float mu = cvec(a, cg, h ? V_RS1 : V_RS0)[i] / hn + cvec(a, cg, V_WMEAN)[i];
-                            B += (mu - mean_all) * (mu - mean_all);
+    if (warp == 0) site_analytics(a, sv, cs, p, lane, (double)clk_chain, (double)clk_lik, (double)n_ticks);
+}
+
+// ---------------------------------------------------------------------------
+// "ping-pong" sampling kernel (tensor-core pass, more sites than SMs): a persistent CTA
+// holds TWO sites.  While the likelihood warps (TMA / tcgen05 / epilogue, the first
+// tc::NTHREADS threads) run the pass of one site, PP_NCW chain warps advance the
+// chains of the other; the roles swap every half-tick, so the tensor-core pipeline
+// and the per-chain dependency chains hide each other.  Finished sites are replaced
+// from a global queue (no wave quantisation).
+// ---------------------------------------------------------------------------
+constexpr int PP_NCW = 4;
+constexpr int PP_THREADS = tc::NTHREADS + 32 * PP_NCW;
+struct PPSlot {
+    int k, state, n_active, n_rows, p;       // state 0 = empty, 1 = sampling
+    uint32_t seed;
+    int64_t row_begin;
+    long long clk_chain, clk_lik, n_ticks;
+};
+__device__ __forceinline__ void chain_group_sync() { asm volatile("bar.sync 2, %0;\n" ::"n"(32 * PP_NCW) : "memory"); }
+
+__global__ void __launch_bounds__(PP_THREADS, 1)
+k_nuts_pp(const SamplerArgs a, const __grid_constant__ CUtensorMap tmap, int n_sites, int* queue) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int C = a.C, d = a.d;
+    __shared__ PPSlot slot[2];
+    __shared__ double lp_lik[2][32];
+    __shared__ int exhausted, go_on[2];
+    const bool lik_thread = tid < tc::NTHREADS;
+    const int cw = warp - tc::NTHREADS / 32, ct = tid - tc::NTHREADS;      // chain warp / thread index
+
+    unsigned char* tcb = smem + ((1024u - (tc::smem_u32(smem) & 1023u)) & 1023u);
+    tc::State tcst;
+    tcst.set_stages(a.tc_nst);
+    const uint32_t tmem_base = tc::setup(tcb, a.tc_nst);
+    if (tid == 0) { slot[0].state = 0; slot[1].state = 0; exhausted = 0; }
+    __syncthreads();
+
+    for (uint32_t h = 0;; ++h) {
+        const int sl = (int)(h & 1u), sc = sl ^ 1;
+        if (lik_thread) {
+            // ---- likelihood pass of slot sl ----
+            if (slot[sl].state == 1) {
+                const long long t0 = clock64();
+                unsigned char* sm = smem + (size_t)sl * a.site_stride;
+                float* om = reinterpret_cast<float*>(sm + a.off_omega);
+                likelihood_pass_tc(a, sm, tcb, tmem_base, &tmap, tcst, slot[sl].k, C, slot[sl].row_begin,
+                                   slot[sl].n_rows, lp_lik[sl], om, om + d * d);
+                if (tid == 0) slot[sl].clk_lik += clock64() - t0;
+            }
+        } else {
+            // ---- chain phase of slot sc (also: retire a finished site, start the next one) ----
+            PPSlot& S = slot[sc];
+            unsigned char* sm = smem + (size_t)sc * a.site_stride;
+            ChainS* cs = reinterpret_cast<ChainS*>(sm + a.off_cs);
+            ChainStack* cstk = reinterpret_cast<ChainStack*>(sm + a.off_cs + sizeof(ChainS) * a.C);
+            float* om = reinterpret_cast<float*>(sm + a.off_omega);
+            for (int round = 0; round < 2; ++round) {
+                if (S.state == 0) {
+                    const int ex = exhausted;
+                    chain_group_sync();                 // everyone has read the flag before thread 0 may set it
+                    if (ex) break;
+                    if (ct == 0) {
+                        const int i = atomicAdd(queue, 1);
+                        if (i < n_sites) {
+                            const int k = a.k0 + i;
+                            S.k = k; S.n_active = C; S.seed = a.seeds[i];
+                            S.row_begin = a.row0[k];
+                            S.n_rows = (int)(a.row0[k + 1] - a.row0[k]);
+                            S.p = model_np(a.model, a.D, 1);
+                            S.clk_chain = 0; S.clk_lik = 0; S.n_ticks = 0;
+                            S.state = 1;
+                        } else {
+                            exhausted = 1;
                         }
                     }
-                    B = B * hn / (m - 1);
-                    const float var_plus = (hn - 1.0f) / hn * W + B / hn;
-                    const float rhat = W > 0.0f ? sqrtf(var_plus / W) : 1.0f;
-                    worst = fmaxf(worst, rhat);
+                    chain_group_sync();
+                    if (S.state == 0) break;
+                    load_cavity(a, S.k, om, ct, 32 * PP_NCW);
+                    init_chains(a, SiteView{sm, S.k}, cs, cw, PP_NCW, lane);
+                    __threadfence_block();
+                    chain_group_sync();
                 }
+                const long long t0 = clock64();
+                const SiteView sv{sm, S.k};
+                chain_phase(a, sv, cs, cstk, lp_lik[sc], &S.n_active, S.p, 1, S.seed, om, om + d * d, cw, PP_NCW, lane);
+                __threadfence_block();
+                chain_group_sync();
+                if (ct == 0) { S.clk_chain += clock64() - t0; S.n_ticks += 1; }
+                if (S.n_active > 0) break;
+                // every chain of the site has finished
+                if (cw == 0) site_analytics(a, sv, cs, S.p, lane, (double)S.clk_chain, (double)S.clk_lik, (double)S.n_ticks);
+                chain_group_sync();
+                if (ct == 0) S.state = 0;
+                chain_group_sync();
             }
+            // (decided by one thread, double-buffered: the slot states change again in the next half-tick)
+            if (ct == 0) go_on[h & 1u] = !(slot[0].state == 0 && slot[1].state == 0 && exhausted);
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) worst = fmaxf(worst, __shfl_xor_sync(0xffffffffu, worst, o));
-        if (lane == 0) {
-            double eps_mean = 0.0, nl = 0.0, nd = 0.0;
-            int ok = 0;
-            for (int c = 0; c < C; ++c) {
-                nl += (double)cs[c].n_leap_total;
-                nd += cs[c].n_div;
-                if (cs[c].phase == PH_DONE) { eps_mean += cs[c].eps_sum / (per > 0 ? per : 1); ++ok; }
-            }
-            double* o = a.out + (size_t)k_local * 8;
-            o[4] = (double)clk_chain; o[5] = (double)clk_lik; o[6] = (double)n_ticks; o[7] = 0.0;
-            o[0] = ok ? eps_mean / ok : NAN;
-            o[1] = (ok == C) ? (double)worst : NAN;
-            o[2] = nl;
-            o[3] = (ok == C) ? nd : -1.0;
-        }
+        __threadfence_block();
+        __syncthreads();
+        if (!go_on[h & 1u]) break;
     }
+    tc::teardown(tmem_base);
 }
 
 // log-density / gradient at caller-supplied points (parity tests)
@@ -1179,12 +1311,15 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) k_logdensity(const SamplerArg
     unsigned char* tcb = smem + ((1024u - (tc::smem_u32(smem) & 1023u)) & 1023u);
     uint32_t tmem_base = 0;
     tc::State tcst;
-    if (a.use_tc) tmem_base = tc::setup(tcb);
+    if (a.use_tc) {
+        tcst.set_stages(a.tc_nst);
+        tmem_base = tc::setup(tcb, a.tc_nst);
+    }
     // the evaluation points were staged in the global copy of V_Q (k_set_q)
     if (worker && a.hot_nvec > V_Q)
         for (int e = tid; e < nq * a.P; e += NTHR) {
             const int c = e / a.P, i = e - c * a.P;
-            cvec(a, k_local * a.C + c, V_Q)[i] = a.chain_mem[((size_t)(k_local * a.C + c) * NVEC + V_Q) * a.P + i];
+            cvec(a, SiteView{smem, k_local}, c, V_Q)[i] = a.chain_mem[((size_t)(k_local * a.C + c) * NVEC + V_Q) * a.P + i];
         }
     __threadfence_block();
     __syncthreads();
@@ -1196,7 +1331,7 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) k_logdensity(const SamplerArg
         likelihood_pass<CP>(a, smem, k_local, k_local, nq, J, row_begin, n_rows, grows, lp_lik, om, muf);
     }
     for (int c = warp; worker && c < nq; c += NWARP) {
-        ChainCtx x = make_chain_ctx(a, k_local * a.C + c, p, d, J, D, lane, make_uint2(0u, 0u), om, muf, nullptr);
+        ChainCtx x = make_chain_ctx(a, SiteView{smem, k_local}, c, p, d, J, D, lane, make_uint2(0u, 0u), om, muf, nullptr);
         const double V = finish_gradient(x, lp_lik[c]);
         const float* g = x.v(V_G);
         if (lane == 0) lp_out[c] = -V;
@@ -1213,10 +1348,11 @@ __global__ void k_set_q(float* chain_mem, int chain0, int P, int p, int nq, cons
 }
 
 // shared-memory plan for a launch
-bool plan_smem(SamplerArgs& a, int CP, int64_t max_rows, int d) {
-    const size_t budget = 227 * 1024 - 1024;
+constexpr size_t SMEM_BUDGET_1 = 227 * 1024 - 1024;       // one CTA per SM
+constexpr size_t SMEM_BUDGET_2 = 112 * 1024 - 256;        // two CTAs per SM: 2 x (dynamic + 1 KB static + 1 KB reserved) <= 228 KB
+bool plan_smem(SamplerArgs& a, int CP, int64_t max_rows, int d, size_t budget = SMEM_BUDGET_1) {
     auto al16 = [](size_t v) { return (v + 15) & ~(size_t)15; };
-    const size_t sz_cs = al16((sizeof(ChainS) + sizeof(ChainStack)) * 32);
+    const size_t sz_cs = al16((sizeof(ChainS) + sizeof(ChainStack)) * (size_t)a.C);
     const size_t sz_om = al16(sizeof(float) * ((size_t)d * d + d));
     const size_t per_vec = sizeof(float) * (size_t)a.C * a.P;          // one hot vector of every chain
     // tail regions shared by both variants: [omega][hot vectors]
@@ -1227,7 +1363,7 @@ bool plan_smem(SamplerArgs& a, int CP, int64_t max_rows, int d) {
         int lv = 0;
         if (nv > V_NHOT) {                      // room left: keep the lowest tree-stack levels on chip too
             lv = (nv - V_NHOT) / 4;
-            if (lv > 4) lv = 4;
+            if (lv > MAXDEPTH_CAP) lv = MAXDEPTH_CAP;
             nv = V_NHOT;
         }
         a.hot_levels = 0;
@@ -1238,7 +1374,8 @@ bool plan_smem(SamplerArgs& a, int CP, int64_t max_rows, int d) {
         return o;
     };
     if (a.use_tc) {
-        size_t o = al16(1024 + tc::Smem::TOTAL);      // 1024: alignment slack for the swizzled tiles
+        if (a.tc_nst < tc::NF || a.tc_nst > tc::NST) a.tc_nst = tc::NST;
+        size_t o = al16(1024 + tc::Smem::total(a.tc_nst));      // 1024: alignment slack for the swizzled tiles
         a.off_E = a.off_B = a.off_G = 0;
         a.R = 0; a.resident = 0; a.slices = 1; a.NC = 1; a.combos = 1;
         a.off_gphi = o; o += al16(sizeof(float) * (size_t)tc::NCH * d);
@@ -1285,6 +1422,41 @@ bool plan_smem(SamplerArgs& a, int CP, int64_t max_rows, int d) {
         if (a.R <= 32) return false;
         a.R /= 2;
     }
+}
+
+// shared-memory plan of the ping-pong kernel: [tensor-core pass buffers][site block 0][site block 1];
+// a site block = [cavc][lp][chain scalars][omega][hot vectors (+ low tree-stack levels)]
+bool plan_smem_pp(SamplerArgs& a, int d) {
+    auto al16 = [](size_t v) { return (v + 15) & ~(size_t)15; };
+    const size_t per_vec = sizeof(float) * (size_t)a.C * a.P;
+    const size_t sz_g = al16(sizeof(float) * (size_t)a.C * d);                // cavity terms of the chains
+    const size_t sz_lp = al16(sizeof(double) * (size_t)NWARP * tc::NCH);
+    const size_t sz_cs = al16((sizeof(ChainS) + sizeof(ChainStack)) * (size_t)a.C);
+    const size_t sz_om = al16(sizeof(float) * ((size_t)d * d + d));
+    const size_t site_min = sz_g + sz_lp + sz_cs + sz_om + al16((size_t)V_NHOT * per_vec);
+    int nst_max = tc::NST;
+    if (const char* e = getenv("EPGPU_NST")) nst_max = std::max(tc::NF, std::min(tc::NST, atoi(e)));
+    for (int nst = nst_max; nst >= tc::NF; --nst) {
+        const size_t tcsz = al16(1024 + tc::Smem::total(nst));
+        if (tcsz + 2 * site_min > SMEM_BUDGET_1) continue;
+        int lv = (int)((SMEM_BUDGET_1 - tcsz - 2 * site_min) / (2 * 4 * per_vec));
+        if (lv > MAXDEPTH_CAP) lv = MAXDEPTH_CAP;
+        a.tc_nst = nst; a.pp = 1;
+        a.off_E = a.off_B = a.off_G = 0;
+        a.R = 0; a.resident = 0; a.slices = 1; a.NC = 1; a.combos = 1;
+        a.omega_smem = 1; a.hot_nvec = V_NHOT; a.hot_levels = lv;
+        size_t o = tcsz;
+        a.off_gphi = 0;                            // (not used by the tensor-core pass)
+        a.off_cavc = o; o += sz_g;
+        a.off_lp = o; o += sz_lp;
+        a.off_cs = o; o += sz_cs;
+        a.off_omega = o; o += sz_om;
+        a.off_hot = o; o += al16((size_t)(V_NHOT + 4 * lv) * per_vec);
+        a.site_stride = o - tcsz;
+        a.smem_total = o + a.site_stride;
+        return true;
+    }
+    return false;
 }
 
 int pad_chains(int C) { return C <= 4 ? 4 : (C <= 8 ? 8 : (C <= 16 ? 16 : 32)); }
@@ -1417,6 +1589,11 @@ int epg_set_option(epg_ctx* c, const char* name, double value) {
         c->sites->use_tc = value != 0.0;
         return 0;
     }
+    if (strcmp(name, "pingpong") == 0) {
+        if (!c->sites) return epg_fail_msg(c, "epg_set_option(pingpong): upload the sites first");
+        c->sites->pp_mode = (int)value;
+        return 0;
+    }
     return epg_fail_msg(c, std::string("epg_set_option: unknown option ") + name);
 }
 
@@ -1425,7 +1602,7 @@ int epg_num_params(epg_ctx* c, int k) {
     return c->sites->h_p[k];
 }
 
-static int fill_args(epg_ctx* c, SamplerArgs& a, int C, int CP) {
+static int fill_args(epg_ctx* c, SamplerArgs& a, int C, int CP, int n_sites = 1) {
     epg_site_data* s = c->sites;
     a.X = s->X; a.y = s->y; a.row0 = s->row0; a.grp_ptr = s->grp_ptr; a.grp_rows = s->grp_rows;
     a.model = s->model; a.D = s->D; a.S = s->S; a.d = c->d;
@@ -1447,9 +1624,26 @@ static int fill_args(epg_ctx* c, SamplerArgs& a, int C, int CP) {
         s->last_q_bytes = need_lq; s->last_C = C;
     }
     EPG_CHECK(c, epg_reserve((void**)&s->omega, &s->omega_bytes, sizeof(float) * (size_t)c->K * (c->d * c->d + c->d)));
-    EPG_CHECK(c, epg_reserve((void**)&s->out, &s->out_bytes, sizeof(double) * (size_t)c->K * 8 + sizeof(uint32_t) * c->K));
+    EPG_CHECK(c, epg_reserve((void**)&s->out, &s->out_bytes, sizeof(double) * (size_t)c->K * 8 + sizeof(uint32_t) * ((size_t)c->K + 4)));
     a.chain_mem = s->chain_mem; a.last_q = s->last_q; a.omega = s->omega; a.out = s->out;
     a.use_tc = (s->tc_ok && s->use_tc && C <= tc::NCH) ? 1 : 0;
+    // More sites than SMs: the ping-pong kernel (two sites per persistent CTA) if both per-site blocks fit.
+    a.tc_nst = tc::NST;
+    a.pp = 0;
+    int mode = s->pp_mode;
+    if (const char* e = getenv("EPGPU_PP")) mode = atoi(e);
+    // (the kernel doubles the number of sites streamed concurrently: it only pays while the bf16 design
+    //  matrices of 2 x SMs sites stay resident in L2 -- measured: config 4, 640 KB per site, does not)
+    const double resident_bytes = 2.0 * c->num_sms * (double)s->max_rows * tc::KW * 2.0;
+    const int pp = a.use_tc && s->Jmax == 1 && n_sites > 1 &&
+                   (mode == 2 || (mode == 1 && n_sites > c->num_sms && resident_bytes <= 0.75 * c->l2_bytes));
+    if (pp && plan_smem_pp(a, c->d)) return 0;
+    a.pp = 0;
+    // the pass is not limited by the depth of the TMA ring, the chain phase is by how many
+    // tree-stack levels stay in shared memory: 4 stages unless everything fits with 8
+    a.tc_nst = tc::NST;
+    if (a.use_tc && plan_smem(a, CP, s->max_rows, c->d) && a.hot_levels < MAXDEPTH_CAP) a.tc_nst = tc::NF;
+    if (const char* e = getenv("EPGPU_NST")) a.tc_nst = atoi(e);
     if (!plan_smem(a, CP, s->max_rows, c->d)) return epg_fail_msg(c, "sampler: shapes exceed the shared-memory plan");
     return 0;
 }
@@ -1472,7 +1666,7 @@ int epg_tilted_sample(epg_ctx* c, int k0, int k1, const uint32_t* seeds, const e
     if (int rc = epg_reserve_draws(c, n)) return rc;
     SamplerArgs a;
     memset(&a, 0, sizeof(a));
-    if (int rc = fill_args(c, a, C, CP)) return rc;
+    if (int rc = fill_args(c, a, C, CP, k1 - k0)) return rc;
     a.iter = o->iter; a.warmup = warm; a.init_mode = o->init_mode;
     a.max_depth = o->max_treedepth > 0 ? std::min(o->max_treedepth, MAXDEPTH_CAP) : 10;
     a.delta = o->adapt_delta > 0 ? o->adapt_delta : 0.8;
@@ -1490,12 +1684,22 @@ int epg_tilted_sample(epg_ctx* c, int k0, int k1, const uint32_t* seeds, const e
     EPG_CHECK(c, cudaEventCreate(&e0));
     EPG_CHECK(c, cudaEventCreate(&e1));
     EPG_CHECK(c, cudaEventRecord(e0, c->stream));
-#define LAUNCH_NUTS(CPV)                                                          \
+#define LAUNCH_NUTS(CPV, TC)                                                      \
     {                                                                             \
-        EPG_CHECK(c, set_smem_attr(k_nuts<CPV>, a.smem_total));                   \
-        k_nuts<CPV><<<k1 - k0, a.use_tc ? tc::NTHREADS : NTHR, a.smem_total, c->stream>>>(a, s->tmap); \
+        EPG_CHECK(c, set_smem_attr(k_nuts<CPV, TC>, a.smem_total));               \
+        k_nuts<CPV, TC><<<k1 - k0, TC ? tc::NTHREADS : NTHR, a.smem_total, c->stream>>>(a, s->tmap); \
     }
-    if (CP == 4) LAUNCH_NUTS(4) else if (CP == 8) LAUNCH_NUTS(8) else if (CP == 16) LAUNCH_NUTS(16) else LAUNCH_NUTS(32)
+    if (a.pp) {
+        int* queue = reinterpret_cast<int*>(dseeds + c->K);
+        EPG_CHECK(c, cudaMemsetAsync(queue, 0, sizeof(int), c->stream));
+        EPG_CHECK(c, set_smem_attr(k_nuts_pp, a.smem_total));
+        int grid = (k1 - k0) > c->num_sms ? c->num_sms : (k1 - k0 + 1) / 2;     // (forced mode: two sites per CTA)
+        if (const char* e = getenv("EPGPU_PP_GRID")) grid = std::max(1, std::min(atoi(e), k1 - k0));
+        k_nuts_pp<<<grid, PP_THREADS, a.smem_total, c->stream>>>(a, s->tmap, k1 - k0, queue);
+    }
+    else if (a.use_tc) LAUNCH_NUTS(32, true)
+    else if (CP == 4) LAUNCH_NUTS(4, false) else if (CP == 8) LAUNCH_NUTS(8, false)
+    else if (CP == 16) LAUNCH_NUTS(16, false) else LAUNCH_NUTS(32, false)
     c->launches++;
     EPG_CHECK(c, cudaGetLastError());
     EPG_CHECK(c, cudaEventRecord(e1, c->stream));
@@ -1528,8 +1732,8 @@ int epg_tilted_sample(epg_ctx* c, int k0, int k1, const uint32_t* seeds, const e
     if (getenv("EPGPU_TRACE")) {
         double cc = 0, cl = 0, nt = 0;
         for (int i = 0; i < k1 - k0; ++i) { cc += out[8 * i + 4]; cl += out[8 * i + 5]; nt += out[8 * i + 6]; }
-        fprintf(stderr, "[epgpu] sampler %d sites: %.3f s, ticks/site %.0f, cycles/tick chain %.0f lik %.0f (tc=%d)\n",
-                k1 - k0, ms * 1e-3, nt / (k1 - k0), cc / nt, cl / nt, a.use_tc);
+        fprintf(stderr, "[epgpu] sampler %d sites: %.3f s, ticks/site %.0f, cycles/tick chain %.0f lik %.0f (tc=%d pp=%d nst=%d levels=%d smem=%zu)\n",
+                k1 - k0, ms * 1e-3, nt / (k1 - k0), cc / nt, cl / nt, a.use_tc, a.pp, a.tc_nst, a.hot_levels, a.smem_total);
     }
     return 0;
 }

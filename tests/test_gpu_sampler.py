@@ -135,6 +135,30 @@ def test_sampler_vs_oracle_nuts(model, J, n, D, C):
     ctx.close()
 
 
+@pytest.mark.parametrize('model,D,C,NS', [('m1b', 6, 8, 7), ('m3b', 5, 4, 10), ('m4b', 19, 3, 5)])
+def test_pingpong_kernel_matches_one_site_per_cta(model, D, C, NS):
+    """The two-sites-per-CTA kernel (used when there are more sites than SMs) runs the same arithmetic and
+    the same counter-based random streams as the one-site-per-CTA kernel: identical draws and analytics,
+    for ragged site sizes and any assignment of sites to CTAs."""
+    sites = [synth.make_site(model, 130 + 97 * k, D, 1, seed=40 + k) for k in range(NS)]
+    ctx = make_ctx(model, sites, use_tc=1)
+    seeds = [17 * (k + 3) for k in range(NS)]
+    iters, warm = 120, 60
+    out = {}
+    for mode in (0, 2):
+        ctx.set_option('pingpong', mode)
+        res = ctx.tilted_sample(seeds, C, iters, warm)
+        out[mode] = (ctx.get_draws(C * (iters - warm)).copy(),) + tuple(np.array(r) for r in res[:3])
+    assert np.all(np.isfinite(out[0][0]))
+    for u, v in zip(out[0], out[2]):
+        assert np.array_equal(u, v)
+    # a sub-range of the sites (k0 > 0) goes through the queue as well
+    ctx.set_option('pingpong', 2)
+    ctx.tilted_sample(seeds[2:], C, iters, warm, k0=2, k1=NS)
+    assert np.array_equal(ctx.get_draws(C * (iters - warm))[2:], out[0][0][2:])
+    ctx.close()
+
+
 def test_init_prev_and_zero_init():
     site = synth.make_site('m1b', 200, 3, 1, seed=5)
     ctx = make_ctx('m1b', [site])
