@@ -40,12 +40,12 @@ constexpr int TMEM_COLS = 256;                       // F buffers [0, NF*32), G 
 constexpr int NBAR = 2 * NST + NF + NE + 1;
 constexpr int NTHREADS = 352;        // warps 0-7: epilogue (two halves x four TMEM lane quarters), 8: GEMM1 issue,
                                      // 9: GEMM2 issue (+ TMEM alloc), 10: TMA producer
-__host__ __device__ constexpr int chain_col(int c) { return (c & 1) * (NCH / 2) + (c >> 1); }
+__host__ __device__ constexpr int chain_col(int c) { return c; }
 
 struct Smem {            // offsets relative to a 1024-byte aligned base
     static constexpr int BM = 0;                     // coefficient operand [32 x 64] (hi rows | lo rows)
-    static constexpr int GOUT = BM + B_BYTES;        // float [NCH][KW]
-    static constexpr int BAR = GOUT + NCH * KW * 4;
+    static constexpr int GOUT = BM + B_BYTES;        // float [2][NCH][KW]: the two row-parity halves of G (summed by the reader)
+    static constexpr int BAR = GOUT + 2 * NCH * KW * 4;
     static constexpr int TMEM_PTR = BAR + NBAR * 8;
     static constexpr int E = (TMEM_PTR + 16 + 1023) & ~1023;          // nst E buffers
     __host__ __device__ static constexpr int X(int nst) { return E + nst * E_BYTES; }     // nst X tiles (1024-aligned)
@@ -144,6 +144,49 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
         : "r"(taddr));
     asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
 }
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t (&r)[4]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+}
+// the hi and lo accumulator columns of one row in a single wait
+template <int N> struct TmemPair;
+template <> struct TmemPair<4> {
+    __device__ static __forceinline__ void ld(uint32_t a_hi, uint32_t a_lo, uint32_t (&h)[4], uint32_t (&l)[4]) {
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%8];\n\t"
+            "tcgen05.ld.sync.aligned.32x32b.x4.b32 {%4,%5,%6,%7}, [%9];\n\t"
+            "tcgen05.wait::ld.sync.aligned;\n"
+            : "=r"(h[0]), "=r"(h[1]), "=r"(h[2]), "=r"(h[3]), "=r"(l[0]), "=r"(l[1]), "=r"(l[2]), "=r"(l[3])
+            : "r"(a_hi), "r"(a_lo) : "memory");
+    }
+};
+template <> struct TmemPair<8> {
+    __device__ static __forceinline__ void ld(uint32_t a_hi, uint32_t a_lo, uint32_t (&h)[8], uint32_t (&l)[8]) {
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%16];\n\t"
+            "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%8,%9,%10,%11,%12,%13,%14,%15}, [%17];\n\t"
+            "tcgen05.wait::ld.sync.aligned;\n"
+            : "=r"(h[0]), "=r"(h[1]), "=r"(h[2]), "=r"(h[3]), "=r"(h[4]), "=r"(h[5]), "=r"(h[6]), "=r"(h[7]),
+              "=r"(l[0]), "=r"(l[1]), "=r"(l[2]), "=r"(l[3]), "=r"(l[4]), "=r"(l[5]), "=r"(l[6]), "=r"(l[7])
+            : "r"(a_hi), "r"(a_lo) : "memory");
+    }
+};
+template <> struct TmemPair<16> {
+    __device__ static __forceinline__ void ld(uint32_t a_hi, uint32_t a_lo, uint32_t (&h)[16], uint32_t (&l)[16]) {
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%32];\n\t"
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%33];\n\t"
+            "tcgen05.wait::ld.sync.aligned;\n"
+            : "=r"(h[0]), "=r"(h[1]), "=r"(h[2]), "=r"(h[3]), "=r"(h[4]), "=r"(h[5]), "=r"(h[6]), "=r"(h[7]),
+              "=r"(h[8]), "=r"(h[9]), "=r"(h[10]), "=r"(h[11]), "=r"(h[12]), "=r"(h[13]), "=r"(h[14]), "=r"(h[15]),
+              "=r"(l[0]), "=r"(l[1]), "=r"(l[2]), "=r"(l[3]), "=r"(l[4]), "=r"(l[5]), "=r"(l[6]), "=r"(l[7]),
+              "=r"(l[8]), "=r"(l[9]), "=r"(l[10]), "=r"(l[11]), "=r"(l[12]), "=r"(l[13]), "=r"(l[14]), "=r"(l[15])
+            : "r"(a_hi), "r"(a_lo) : "memory");
+    }
+};
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
@@ -156,6 +199,16 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 // byte offset of element (n, k) of a K-major INTERLEAVE (no swizzle) operand with
 // NCH rows: 8x(16 B) core matrices, the two row groups adjacent (SBO = 128 B),
 // K chunks of 8 elements LBO = 256 B apart
+// byte offset of E element (chain n, tile row rho) in an E buffer.  GEMM2 runs as 4 instructions of
+// M = 128, N = 32, K = 16 per tile: instruction i covers rows [32i, 32i+32); its A operand stacks the X'
+// slices of rows 32i..32i+15 (M block 0) and 32i+16..32i+31 (M block 1, LBO = 16 rows), its B operand the
+// matching E slices as N block 0 / N block 1 -- the two diagonal blocks of the 128 x 32 accumulator are the
+// wanted products, so one instruction does the work of two K = 16 steps.  B is a K-major INTERLEAVE operand:
+// 8x(16 B) core matrices, the four 8-row groups 128 B apart (SBO), the two K chunks 512 B apart (LBO).
+__device__ __forceinline__ int e_off(int n, int rho) {
+    return (rho >> 5) * 1024 + ((rho >> 3) & 1) * 512 + ((((rho >> 4) & 1) << 1) + (n >> 3)) * 128 + (n & 7) * 16 +
+           (rho & 7) * 2;
+}
 __device__ __forceinline__ int interleave_off(int n, int k) {
     return (k >> 3) * 256 + (n >> 3) * 128 + (n & 7) * 16 + (k & 7) * 2;
 }
@@ -179,11 +232,13 @@ __device__ inline uint32_t setup(unsigned char* base, int nst) {
     if (tid == 0) {
         for (int i = 0; i < NST; ++i) { mbar_init(B.full + i, 1); mbar_init(B.empty + i, 1); }
         for (int i = 0; i < NF; ++i) mbar_init(B.fready + i, 1);
-        for (int i = 0; i < NE; ++i) mbar_init(B.eready + i, 256);
+        for (int i = 0; i < NE; ++i) mbar_init(B.eready + i, 128);      // one epilogue group (4 warps) per tile
         mbar_init(B.gready, 1);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     for (int e = tid; e < nst * E_BYTES / 4; e += blockDim.x) reinterpret_cast<uint32_t*>(base + Smem::E)[e] = 0u;
+    for (int e = tid; e < B_BYTES / 4; e += blockDim.x) reinterpret_cast<uint32_t*>(base + Smem::BM)[e] = 0u;
+    fence_proxy_async();                 // the zeros are read by the tensor core (async proxy)
     if ((tid >> 5) == 9) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n"
                      ::"r"(smem_u32(base + Smem::TMEM_PTR)), "n"(TMEM_COLS) : "memory");
@@ -211,6 +266,21 @@ struct State {
 __device__ __forceinline__ void ring_next(uint32_t nst, uint32_t& slot, uint32_t& use) {
     if (++slot == nst) { slot = 0; ++use; }
 }
+#ifdef EPG_TC_EXPERIMENT
+__device__ int g_knobs;          // bit 0: no TMA after the first ring fill, 1: GEMM1 one k-step, 2: GEMM2 one instruction, 3: no logistic math
+#define KNOB(b) (tc::g_knobs & (1 << (b)))
+#else
+#define KNOB(b) 0
+#endif
+#ifdef EPG_TC_TIMELINE
+__device__ long long g_tl[8][64];        // event timeline of one pass (block 0, tick 300): [event][tile]
+__device__ long long g_tlx[8];           // pass start, prologue end, tiles done, gready seen, end
+#define TL(ev, t) if (blockIdx.x == 0 && st.ticks == 300 && (t) < 64) tc::g_tl[ev][t] = clock64()
+#define TLX(i) if (blockIdx.x == 0 && st.ticks == 300) tc::g_tlx[i] = clock64()
+#else
+#define TL(ev, t)
+#define TLX(i)
+#endif
 #ifdef EPG_TC_PROFILE
 __device__ long long g_prof[8];
 #define PROF_T(var) const long long var = clock64()
@@ -227,10 +297,10 @@ __device__ long long g_prof2[8];
 // operands (B_hi, B_lo) with interleave_off(chain_col(c), k) and executed
 // fence_proxy_async + __syncthreads.  Returns with G (likelihood gradient wrt the
 // 64 coefficient columns, [NCH columns][KW] floats) in smem at Smem::GOUT and the
-// lp partial sums per warp in `lpw` ([8 warps][NCH/2] doubles; warp w covers the
-// columns of half w>>2).  All NTHREADS threads must call it; the caller follows
-// with a __syncthreads.  NCPH = columns each epilogue half really processes.
-template <int NCPH, class Prologue>
+// lp partial sums per warp in `lpw` ([8 warps][NCH] doubles, columns < NCP).  All
+// NTHREADS threads must call it; the caller follows with a barrier over them.
+// NCP = chain columns really processed (chains padded to 4, 8 or 16).
+template <int NCP, class Prologue>
 __device__ inline void pass(unsigned char* base, uint32_t tmem_base, const CUtensorMap* tmap, State& st,
                             int64_t row_begin, int n_rows, int ksteps, const float* __restrict__ yglob, double* lpw,
                             Prologue&& prologue) {
@@ -242,17 +312,21 @@ __device__ inline void pass(unsigned char* base, uint32_t tmem_base, const CUten
     const int x_off = Smem::X((int)nst);
     const uint32_t xs = smem_u32(base + x_off);
     constexpr uint32_t IDESC1 = make_idesc(128, NB1, 0);
-    constexpr uint32_t IDESC2 = make_idesc(64, NCH, 1);
+    constexpr uint32_t IDESC2 = make_idesc(128, 2 * NCH, 1);
 
     if (warp == 10) {
         // ===== TMA producer (warp runs converged; one elected lane issues) =====
         uint32_t slot = st.slot, use = st.use;
         for (int t = 0; t < n_tiles; ++t, ring_next(nst, slot, use)) {
             if (use > 0) mbar_wait(B.empty + slot, (use - 1) & 1);     // GEMM2 of the previous user is done
+            if (lane == 0) { TL(0, t); }
             if (elect_one()) {
+                if (KNOB(0) && st.tiles + t >= nst) mbar_arrive(B.full + slot);
+                else {
                 mbar_expect_tx(B.full + slot, TILE_BYTES);
                 tma_load_2d(base + x_off + slot * TILE_BYTES, tmap, B.full + slot, 0,
                             (int)(row_begin + (int64_t)t * TILE_M));
+                }
             }
             __syncwarp();
         }
@@ -269,15 +343,17 @@ __device__ inline void pass(unsigned char* base, uint32_t tmem_base, const CUten
             }
             mbar_wait(B.full + slot, use & 1);
             tc_fence_after();
+            if (lane == 0) { TL(1, t); }
             const uint64_t xa_d = make_desc(xs + slot * TILE_BYTES, 16, 1024, 2);
             const uint32_t dF = tmem_base + fb * NB1;
             if (elect_one()) {
 #pragma unroll
                 for (int ks = 0; ks < KW / 16; ++ks)          // start-address field is in 16-byte units
-                    if (ks < ksteps) umma(dF, xa_d + (uint64_t)(ks * 2), bm_d + (uint64_t)(ks * 64), IDESC1, ks > 0);
+                    if (ks < (KNOB(1) ? 1 : ksteps)) umma(dF, xa_d + (uint64_t)(ks * 2), bm_d + (uint64_t)(ks * 64), IDESC1, ks > 0);
                 umma_commit(B.fready + fb);
             }
             __syncwarp();
+            if (lane == 0) { TL(2, t); }
         }
     } else if (warp == 9) {
         // ===== GEMM2 issuer (warp runs converged; one elected lane issues) =====
@@ -289,58 +365,68 @@ __device__ inline void pass(unsigned char* base, uint32_t tmem_base, const CUten
             mbar_wait(B.eready + eb_i, use & 1);
             tc_fence_after();
             PROF_T(m1);
-            const uint64_t xa_d = make_desc(xs + slot * TILE_BYTES, 1024, 1024, 2);
-            const uint64_t ea_d = make_desc(eb + eb_i * E_BYTES, 256, 128, 0);
+            if (lane == 0) { TL(5, t); }
+            // A = X_tile' (MN-major, SW128): second 64-element M block = 16 rows further (LBO 2048 B),
+            // 8-row K groups 1024 B apart (SBO); B = E (see e_off)
+            const uint64_t xa_d = make_desc(xs + slot * TILE_BYTES, 2048, 1024, 2);
+            const uint64_t ea_d = make_desc(eb + eb_i * E_BYTES, 512, 128, 0);
             const uint32_t acc0 = t > 0 ? 1u : 0u;
             if (elect_one()) {
 #pragma unroll
-                for (int ks = 0; ks < TILE_M / 16; ++ks)
-                    // A = X_tile' (MN-major, SW128): 16 rows further = +2048 B;  B = E: 2 K-chunks = +512 B
-                    umma(tmem_base + NF * NB1, xa_d + (uint64_t)(ks * 128), ea_d + (uint64_t)(ks * 32), IDESC2,
-                         ks > 0 ? 1u : acc0);
+                for (int i = 0; i < (KNOB(2) ? 1 : TILE_M / 32); ++i)
+                    // 32 rows further: A + 4096 B, B + 1024 B (start-address field is in 16-byte units)
+                    umma(tmem_base + NF * NB1, xa_d + (uint64_t)(i * 256), ea_d + (uint64_t)(i * 64), IDESC2,
+                         i > 0 ? 1u : acc0);
                 umma_commit(B.empty + slot);
             }
             __syncwarp();
             PROF_T(m3);
+            if (lane == 0) { TL(6, t); }
             if (lane == 0) { PROF2_ADD(0, m0, m1); PROF2_ADD(1, m1, m3); PROF2_ADD(7, 0, 1); }
         }
         if (elect_one()) umma_commit(B.gready);
         __syncwarp();
     } else {
-        // ===== epilogue: one row of the tile per thread, half of the columns per warp group =====
+        // ===== epilogue: one row of the tile per thread, all NCP chain columns; the two groups of four
+        //       warps take alternate tiles, so that two tiles' load -> logistic -> store -> fence chains overlap =====
         const int q = warp & 3;                       // TMEM lane quarter this warp may access
-        const int half = warp >> 2;                   // columns [half*8, half*8+8)
+        const int grp = warp >> 2;                    // tiles t with (t & 1) == grp
         const int r = q * 32 + lane;                  // row within the tile
-        const int col0 = half * (NCH / 2);
+        if (tid == 0) { TLX(0); }
         prologue();                                   // independent work that hides the pipeline fill
-        float lpacc[NCPH];
+        if (tid == 0) { TLX(1); }
+        float lpacc[NCP];
 #pragma unroll
-        for (int c = 0; c < NCPH; ++c) lpacc[c] = 0.0f;
-        float y_next = (r < n_rows) ? yglob[row_begin + r] : 0.0f;
+        for (int c = 0; c < NCP; ++c) lpacc[c] = 0.0f;
         uint32_t ebi = st.slot, euse = st.use;
-        for (int t = 0; t < n_tiles; ++t, ring_next(nst, ebi, euse)) {
+        if (grp) ring_next(nst, ebi, euse);
+        float y_next = (grp * TILE_M + r < n_rows) ? yglob[row_begin + grp * TILE_M + r] : 0.0f;
+        for (int t = grp; t < n_tiles; t += 2, ring_next(nst, ebi, euse), ring_next(nst, ebi, euse)) {
             const uint32_t gt = t0 + t, fb = gt % NF;
             const int row = t * TILE_M + r;
             const float keep = row < n_rows ? 1.0f : 0.0f;
             const float yv = y_next;
-            {   // prefetch the next tile's response while this tile is processed
-                const int rn = row + TILE_M;
-                y_next = (rn < n_rows) ? yglob[row_begin + rn] : 0.0f;
+            {   // prefetch this group's next tile's response while this tile is processed
+                const int rn = row + 2 * TILE_M;
+                y_next = yglob[row_begin + (rn < n_rows ? rn : n_rows - 1)];      // (clamped: unused when out of range)
             }
             PROF_T(p0);
             mbar_wait(B.fready + fb, (gt / NF) & 1);
             tc_fence_after();
             PROF_T(p1);
-            uint32_t fr[8], fl[8];
-            tmem_ld8(tmem_base + ((uint32_t)(q * 32) << 16) + fb * NB1 + col0, fr);
-            tmem_ld8(tmem_base + ((uint32_t)(q * 32) << 16) + fb * NB1 + NCH + col0, fl);
+            if (lane == 0 && q == 0) { TL(3, t); }
+            uint32_t fr[NCP], fl[NCP];
+            TmemPair<NCP>::ld(tmem_base + ((uint32_t)(q * 32) << 16) + fb * NB1,
+                              tmem_base + ((uint32_t)(q * 32) << 16) + fb * NB1 + NCH, fr, fl);
             tc_fence_before();
             PROF_T(p2);
-            __nv_bfloat16 ev[NCPH];
+            __nv_bfloat16 ev[NCP];
 #pragma unroll
-            for (int c = 0; c < NCPH; ++c) {
+            for (int c = 0; c < NCP; ++c) {
                 float e;
-                const float l = logit_terms(__uint_as_float(fr[c]) + __uint_as_float(fl[c]), yv, e);
+                float l;
+                if (KNOB(3)) { e = __uint_as_float(fr[c]); l = __uint_as_float(fl[c]); }
+                else l = logit_terms(__uint_as_float(fr[c]) + __uint_as_float(fl[c]), yv, e);
                 lpacc[c] = fmaf(keep, l, lpacc[c]);
                 ev[c] = __float2bfloat16(keep * e);
             }
@@ -348,36 +434,41 @@ __device__ inline void pass(unsigned char* base, uint32_t tmem_base, const CUten
             PROF_T(p4);                       // (E buffer ebi is free: see NE)
             unsigned char* eb = base + Smem::E + ebi * E_BYTES;
 #pragma unroll
-            for (int c = 0; c < NCPH; ++c)
-                *reinterpret_cast<__nv_bfloat16*>(eb + interleave_off(col0 + c, r)) = ev[c];
+            for (int c = 0; c < NCP; ++c)
+                *reinterpret_cast<__nv_bfloat16*>(eb + e_off(c, r)) = ev[c];
             PROF_T(p5);
             fence_proxy_async();
             PROF_T(p6);
             mbar_arrive(B.eready + ebi);
             PROF_T(p7);
+            if (lane == 0 && q == 0) { TL(4, t); }
             PROF_ADD(0, p0, p1); PROF_ADD(1, p1, p2); PROF_ADD(2, p2, p3); PROF_ADD(3, p3, p4);
             PROF_ADD(4, p4, p5); PROF_ADD(5, p5, p6); PROF_ADD(6, p6, p7);
 #ifdef EPG_TC_PROFILE
             if (threadIdx.x == 0 && blockIdx.x == 0) g_prof[7] += 1;
 #endif
         }
+        if (tid == 0) { TLX(2); }
         // lp partial sums (fp64 across the warp)
 #pragma unroll
-        for (int c = 0; c < NCPH; ++c) {
+        for (int c = 0; c < NCP; ++c) {
             const double v = warp_sum((double)lpacc[c]);
-            if (lane == 0) lpw[warp * (NCH / 2) + c] = v;
+            if (lane == 0) lpw[warp * NCH + c] = v;
         }
-        // G: rows 16q..16q+15 of the 64 coefficient columns sit in lanes 0..15 of quarter q
+        // G read-out.  Accumulator [128 lanes x 32 columns]: lanes 0..63 x columns 0..15 hold the sum over the
+        // rows with (row & 16) == 0, lanes 64..127 x columns 16..31 the sum over the others; lane & 63 is the
+        // coefficient column.  Warp (q, grp) reads 8 chain columns of its lane quarter.
         mbar_wait(B.gready, st.ticks & 1);
         tc_fence_after();
+        if (tid == 0) { TLX(3); }
+        const int hsel = q >> 1;
         uint32_t gr[8];
-        tmem_ld8(tmem_base + ((uint32_t)(q * 32) << 16) + NF * NB1 + col0, gr);
+        tmem_ld8(tmem_base + ((uint32_t)(q * 32) << 16) + NF * NB1 + hsel * NCH + grp * 8, gr);
         tc_fence_before();
-        float* gout = reinterpret_cast<float*>(base + Smem::GOUT);
-        if (lane < 16) {
+        float* gout = reinterpret_cast<float*>(base + Smem::GOUT) + hsel * NCH * KW;
 #pragma unroll
-            for (int c = 0; c < NCH / 2; ++c) gout[(col0 + c) * KW + q * 16 + lane] = __uint_as_float(gr[c]);
-        }
+        for (int c = 0; c < 8; ++c) gout[(grp * 8 + c) * KW + (q & 1) * 32 + lane] = __uint_as_float(gr[c]);
+        if (tid == 0) { TLX(4); }
     }
     st.tiles += (uint32_t)n_tiles;
     st.ticks += 1;

@@ -51,7 +51,7 @@ struct epg_site_data {
     CUtensorMap tmap;                   // TMA descriptor of Xb: box 64 x 128 rows, 128-byte swizzle
     bool tc_ok = false;                 // tensor-core pass usable (single group, D+1 <= 64)
     int use_tc = 1;                     // option (epg_set_option "use_tc")
-    int pp_mode = 1;                    // option "pingpong": 0 never, 1 when sites > SMs, 2 always (tests)
+    int pp_mode = 0;                    // option "pingpong": 0 never (default), 1 when sites > SMs and L2-resident, 2 always
     float* y = nullptr;                 // [N]
     int64_t* row0 = nullptr;            // [K+1]
     int* grp_ptr = nullptr;             // [K+1] offsets into grp_rows
@@ -251,13 +251,20 @@ __device__ __forceinline__ void cavity_term(const SamplerArgs& a, unsigned char*
     for (int e = threadIdx.x; e < nchains * d; e += nthr_workers) {
         const int c = e / d, i = e - c * d;
         const float* q = cvec(a, SiteView{smem, k_local}, c, V_Q);
-        float acc0 = 0.0f, acc1 = 0.0f;
+        // eight independent loads and four accumulators per step: the loop is latency-bound otherwise
+        float acc0 = 0.0f, acc1 = 0.0f, acc2 = 0.0f, acc3 = 0.0f;
+        const float* oc = om + i;
         int j = 0;
-        for (; j + 1 < d; j += 2) {
-            acc0 = fmaf(om[i + (size_t)j * d], q[j] - muf[j], acc0);
-            acc1 = fmaf(om[i + (size_t)(j + 1) * d], q[j + 1] - muf[j + 1], acc1);
+        for (; j + 3 < d; j += 4) {
+            const float o0 = oc[(size_t)j * d], o1 = oc[(size_t)(j + 1) * d];
+            const float o2 = oc[(size_t)(j + 2) * d], o3 = oc[(size_t)(j + 3) * d];
+            const float x0 = q[j] - muf[j], x1 = q[j + 1] - muf[j + 1];
+            const float x2 = q[j + 2] - muf[j + 2], x3 = q[j + 3] - muf[j + 3];
+            acc0 = fmaf(o0, x0, acc0); acc1 = fmaf(o1, x1, acc1);
+            acc2 = fmaf(o2, x2, acc2); acc3 = fmaf(o3, x3, acc3);
         }
-        if (j < d) acc0 = fmaf(om[i + (size_t)j * d], q[j] - muf[j], acc0);
+        for (; j < d; ++j) acc0 = fmaf(oc[(size_t)j * d], q[j] - muf[j], acc0);
+        acc0 += acc2; acc1 += acc3;
         cavc[e] = acc0 + acc1;
     }
 }
@@ -485,10 +492,10 @@ __device__ void likelihood_pass_tc(const SamplerArgs& a, unsigned char* smem, un
     PROF_T(q0);
     if (worker) {
         // coefficient operands B = B_hi + B_lo (bf16 each), K-major interleaved layout
-        for (int e = tid; e < tc::NCH * tc::KW; e += NTHR) {
+        for (int e = tid; e < nchains * tc::KW; e += NTHR) {       // (rows of unused chains stay zero from setup)
             const int c = e / tc::KW, col = e - c * tc::KW;
             float v = 0.0f;
-            if (c < nchains && col <= D) {
+            if (col <= D) {
                 const float* q = cvec(a, SiteView{smem, k_local}, c, V_Q);
                 if (col == D) v = q[d] * __expf(q[ia]) + (model == EPG_M4B ? q[0] : 0.0f);
                 else if (model == EPG_M1B) v = q[1 + col];
@@ -508,19 +515,19 @@ __device__ void likelihood_pass_tc(const SamplerArgs& a, unsigned char* smem, un
     // the cavity term is independent of the pass: the epilogue warps compute it while the
     // first tiles are in flight
     auto prologue = [&]() { cavity_term(a, smem, om, muf, k_local, nchains, NTHR); };
-    if (nchains <= 4) tc::pass<2>(tcb, tmem_base, tmap, st, row_begin, n_rows, ksteps, a.y, lpw, prologue);
-    else if (nchains <= 8) tc::pass<4>(tcb, tmem_base, tmap, st, row_begin, n_rows, ksteps, a.y, lpw, prologue);
-    else tc::pass<8>(tcb, tmem_base, tmap, st, row_begin, n_rows, ksteps, a.y, lpw, prologue);
+    if (nchains <= 4) tc::pass<4>(tcb, tmem_base, tmap, st, row_begin, n_rows, ksteps, a.y, lpw, prologue);
+    else if (nchains <= 8) tc::pass<8>(tcb, tmem_base, tmap, st, row_begin, n_rows, ksteps, a.y, lpw, prologue);
+    else tc::pass<16>(tcb, tmem_base, tmap, st, row_begin, n_rows, ksteps, a.y, lpw, prologue);
     PROF_T(q2);
     lik_group_sync();
     PROF_T(q3);
     if (worker) {
         // chain rule (single group: every slot of the likelihood gradient gets exactly one term)
         const float* gout = reinterpret_cast<const float*>(tcb + tc::Smem::GOUT);
-        for (int e = tid; e < tc::NCH * tc::KW; e += NTHR) {
+        for (int e = tid; e < nchains * tc::KW; e += NTHR) {
             const int c = e / tc::KW, col = e - c * tc::KW;
-            if (c >= nchains || col > D) continue;
-            const float gsum = gout[tc::chain_col(c) * tc::KW + col];
+            if (col > D) continue;
+            const float gsum = gout[tc::chain_col(c) * tc::KW + col] + gout[(tc::NCH + tc::chain_col(c)) * tc::KW + col];
             const float* q = cvec(a, SiteView{smem, k_local}, c, V_Q);
             float* gl = cvec(a, SiteView{smem, k_local}, c, V_GL);
             if (col == D) {
@@ -539,10 +546,8 @@ __device__ void likelihood_pass_tc(const SamplerArgs& a, unsigned char* smem, un
             }
         }
         if (tid < nchains) {
-            // chain c lives in half (c & 1), slot (c >> 1): warps 4*half .. 4*half+3
-            const int half = tid & 1, slot = tid >> 1;
             double sum = 0.0;
-            for (int w = 4 * half; w < 4 * half + 4; ++w) sum += lpw[w * (tc::NCH / 2) + slot];
+            for (int w = 0; w < NWARP; ++w) sum += lpw[w * tc::NCH + tc::chain_col(tid)];
             lp_out[tid] = sum;
         }
     }
@@ -1364,6 +1369,7 @@ bool plan_smem(SamplerArgs& a, int CP, int64_t max_rows, int d, size_t budget = 
         if (nv > V_NHOT) {                      // room left: keep the lowest tree-stack levels on chip too
             lv = (nv - V_NHOT) / 4;
             if (lv > MAXDEPTH_CAP) lv = MAXDEPTH_CAP;
+            if (const char* e = getenv("EPGPU_LEVELS")) lv = std::min(lv, atoi(e));
             nv = V_NHOT;
         }
         a.hot_levels = 0;
@@ -1639,10 +1645,18 @@ static int fill_args(epg_ctx* c, SamplerArgs& a, int C, int CP, int n_sites = 1)
                    (mode == 2 || (mode == 1 && n_sites > c->num_sms && resident_bytes <= 0.75 * c->l2_bytes));
     if (pp && plan_smem_pp(a, c->d)) return 0;
     a.pp = 0;
-    // the pass is not limited by the depth of the TMA ring, the chain phase is by how many
-    // tree-stack levels stay in shared memory: 4 stages unless everything fits with 8
-    a.tc_nst = tc::NST;
-    if (a.use_tc && plan_smem(a, CP, s->max_rows, c->d) && a.hot_levels < MAXDEPTH_CAP) a.tc_nst = tc::NF;
+    // Ring depth vs tree-stack levels in shared memory (measured on config 4): the pass gains up to 5 stages
+    // (29.2k -> 25.4k cycles per tick), the chain phase up to 5 levels (12.3k -> 7.3k): take the deepest ring
+    // that still leaves 5 levels (or all the sampler can use) on chip.
+    a.tc_nst = tc::NF;
+    if (a.use_tc) {
+        const int want = std::min(5, std::min(MAXDEPTH_CAP, a.max_depth > 0 ? a.max_depth : 10));
+        for (int nst = tc::NST; nst > tc::NF; --nst) {
+            a.tc_nst = nst;
+            if (plan_smem(a, CP, s->max_rows, c->d) && a.hot_nvec >= V_NHOT && a.hot_levels >= want) break;
+            a.tc_nst = tc::NF;
+        }
+    }
     if (const char* e = getenv("EPGPU_NST")) a.tc_nst = atoi(e);
     if (!plan_smem(a, CP, s->max_rows, c->d)) return epg_fail_msg(c, "sampler: shapes exceed the shared-memory plan");
     return 0;
@@ -1680,6 +1694,9 @@ int epg_tilted_sample(epg_ctx* c, int k0, int k1, const uint32_t* seeds, const e
     EPG_CHECK(c, cudaMemcpyAsync(dseeds, seeds, sizeof(uint32_t) * (k1 - k0), cudaMemcpyHostToDevice, c->stream));
     a.seeds = dseeds;
     a.draws = c->draws; a.n_draws = n; a.k0 = k0;
+#ifdef EPG_TC_EXPERIMENT
+    { int kn = getenv("EPGPU_KNOBS") ? atoi(getenv("EPGPU_KNOBS")) : 0; cudaMemcpyToSymbol(tc::g_knobs, &kn, sizeof(int)); }
+#endif
     cudaEvent_t e0, e1;
     EPG_CHECK(c, cudaEventCreate(&e0));
     EPG_CHECK(c, cudaEventCreate(&e1));
@@ -1728,6 +1745,23 @@ int epg_tilted_sample(epg_ctx* c, int k0, int k1, const uint32_t* seeds, const e
         fprintf(stderr, "[epgpu] mma thread cycles/tile: wait_e %.0f issue_g2 %.0f commits %.0f gemm1(wait full+issue) %.0f (tiles %lld)\n",
                 (double)hp[0] / hp[7], (double)hp[1] / hp[7], (double)hp[2] / hp[7], (double)hp[3] / hp[7], hp[7]);
     }
+#endif
+#ifdef EPG_TC_TIMELINE
+    if (getenv("EPGPU_TRACE"))
+        {
+            long long tl[8][64], tx[8];
+            cudaMemcpyFromSymbol(tl, tc::g_tl, sizeof(tl));
+            cudaMemcpyFromSymbol(tx, tc::g_tlx, sizeof(tx));
+            const long long z = tx[0];
+            fprintf(stderr, "[epgpu] timeline (cycles from pass start): prologue_end %lld tiles_done %lld gready %lld end %lld\n",
+                    tx[1] - z, tx[2] - z, tx[3] - z, tx[4] - z);
+            fprintf(stderr, "[epgpu] tile: tma_issue full_seen g1_issued f_seen e_arrived e_seen g2_issued\n");
+            for (int t = 0; t < 44; ++t) {
+                fprintf(stderr, "[epgpu] %2d:", t);
+                for (int e = 0; e < 7; ++e) fprintf(stderr, " %7lld", tl[e][t] ? tl[e][t] - z : -1);
+                fprintf(stderr, "\n");
+            }
+        }
 #endif
     if (getenv("EPGPU_TRACE")) {
         double cc = 0, cl = 0, nt = 0;

@@ -178,9 +178,10 @@ int epg_tilted_sample(epg_ctx* ctx, int k0, int k1, const uint32_t* seeds,
 
 /* Options.  "use_tc" (default 1): use the tcgen05/TMA likelihood pass when the
  * shapes allow it (single-group sites, D+1 <= 64, chains <= 16); 0 forces the
- * fp32 SIMT pass.  "pingpong" (default 1): with the tensor-core pass and more
- * sites than SMs, run the persistent two-sites-per-CTA kernel (likelihood pass of
- * one site overlapped with the chain phase of the other); 0 = never, 2 = always.
+ * fp32 SIMT pass.  "pingpong" (default 0): 1 = with the tensor-core pass, more
+ * sites than SMs and design matrices that stay L2-resident, run the persistent
+ * two-sites-per-CTA kernel (likelihood pass of one site overlapped with the chain
+ * phase of the other); 2 = always; 0 = never (measured gain on B200 is <= 15 %).
  * Draws do not depend on these two kernels' choice.  Call after epg_upload_sites. */
 int epg_set_option(epg_ctx* ctx, const char* name, double value);
 
