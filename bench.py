@@ -347,7 +347,12 @@ def main():
         'clocks': clk,
         'roofline': {'bound': 'tensor', 'achieved': tf_achieved, 'peak': tf_peak, 'unit': 'TFLOP/s',
                      'frac': tf_achieved / tf_peak, 'traffic': None, 'kernel': 'k_nuts',
-                     'peak_source': peak_src + ' bf16 sustained; contractions on tcgen05 (bf16 in, fp32 accumulate)'},
+                     'peak_source': peak_src + ' bf16 sustained; contractions on tcgen05 (bf16 in, fp32 accumulate)',
+                     # supplementary view: every gradient evaluation of a site's chains streams the site's bf16
+                     # design matrix (64 padded columns) + responses once, from L2 (the tile phase is
+                     # bound by shared-memory bandwidth, 3 crossings per tile)
+                     'x_stream': {'achieved': (n_leap / chains / max(world, 1)) * n_k * (64 * 2 + 4) / max(samp_s, 1e-9) / 1e9,
+                                  'unit': 'GB/s per GPU (L2 -> shared memory)', 'hbm_peak': hbm_peak}},
         'info': int(info), 'mean_stepsize': float(np.mean(msteps)), 'max_rhat': float(np.max(mrhats)),
     }
     if not args.no_cpu_baseline:

@@ -209,7 +209,7 @@ struct SamplerArgs {
 
 // One site as a CTA sees it: its index and the base of its block of shared memory (the per-site offsets of
 // SamplerArgs are relative to `sm`; the ping-pong kernel keeps two such blocks).
-struct SiteView { unsigned char* sm; int k; };
+struct SiteView { unsigned char* sm; int k; uint32_t off = 0; };   // off: sm minus the start of dynamic shared memory
 
 __device__ __forceinline__ float* cvec(const SamplerArgs& a, const SiteView& sv, int c_local, int v) {
     const bool hot = v < a.hot_nvec;
@@ -242,30 +242,55 @@ __device__ __forceinline__ float logit_terms(float f, float yv, float& e) {
 
 #include "epg_lik_tc.cuh"
 
+// shared-memory load through the shared window (ld.shared).  The pointers the sampler works with are generic
+// (a vector lives in shared OR global memory depending on the launch plan), and generic loads take the L1TEX
+// path: measured ~200 cycles per dependent step against ~30 for ld.shared.  Only for data that no thread
+// writes while the caller runs (no memory clobber: the compiler may schedule the loads freely).
+__device__ __forceinline__ float lds_ro(uint32_t saddr) {
+    float v;
+    asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(saddr));
+    return v;
+}
+
 // Cavity term of every chain, c = Omega (phi - mu), by the whole CTA (one (chain,row)
 // dot product per thread) into shared memory; consumed by finish_gradient.
 __device__ __forceinline__ void cavity_term(const SamplerArgs& a, unsigned char* smem, const float* om, const float* muf,
                                             int k_local, int nchains, int nthr_workers) {
     float* cavc = reinterpret_cast<float*>(smem + a.off_cavc);
     const int d = a.d;
+    const bool in_smem = a.omega_smem && a.hot_nvec > V_Q;
     for (int e = threadIdx.x; e < nchains * d; e += nthr_workers) {
         const int c = e / d, i = e - c * d;
         const float* q = cvec(a, SiteView{smem, k_local}, c, V_Q);
         // eight independent loads and four accumulators per step: the loop is latency-bound otherwise
         float acc0 = 0.0f, acc1 = 0.0f, acc2 = 0.0f, acc3 = 0.0f;
-        const float* oc = om + i;
         int j = 0;
-        for (; j + 3 < d; j += 4) {
-            const float o0 = oc[(size_t)j * d], o1 = oc[(size_t)(j + 1) * d];
-            const float o2 = oc[(size_t)(j + 2) * d], o3 = oc[(size_t)(j + 3) * d];
-            const float x0 = q[j] - muf[j], x1 = q[j + 1] - muf[j + 1];
-            const float x2 = q[j + 2] - muf[j + 2], x3 = q[j + 3] - muf[j + 3];
-            acc0 = fmaf(o0, x0, acc0); acc1 = fmaf(o1, x1, acc1);
-            acc2 = fmaf(o2, x2, acc2); acc3 = fmaf(o3, x3, acc3);
+        if (in_smem) {
+            const uint32_t oc = tc::smem_u32(om + i), qs = tc::smem_u32(q), ms = tc::smem_u32(muf);
+            const uint32_t dd = 4u * (uint32_t)d;
+            for (; j + 3 < d; j += 4) {
+                const uint32_t ob = oc + (uint32_t)j * dd, jb = 4u * (uint32_t)j;
+                const float o0 = lds_ro(ob), o1 = lds_ro(ob + dd), o2 = lds_ro(ob + 2 * dd), o3 = lds_ro(ob + 3 * dd);
+                const float x0 = lds_ro(qs + jb) - lds_ro(ms + jb), x1 = lds_ro(qs + jb + 4) - lds_ro(ms + jb + 4);
+                const float x2 = lds_ro(qs + jb + 8) - lds_ro(ms + jb + 8), x3 = lds_ro(qs + jb + 12) - lds_ro(ms + jb + 12);
+                acc0 = fmaf(o0, x0, acc0); acc1 = fmaf(o1, x1, acc1);
+                acc2 = fmaf(o2, x2, acc2); acc3 = fmaf(o3, x3, acc3);
+            }
+            for (; j < d; ++j)
+                acc0 = fmaf(lds_ro(oc + (uint32_t)j * dd), lds_ro(qs + 4u * j) - lds_ro(ms + 4u * j), acc0);
+        } else {
+            const float* oc = om + i;
+            for (; j + 3 < d; j += 4) {
+                const float o0 = oc[(size_t)j * d], o1 = oc[(size_t)(j + 1) * d];
+                const float o2 = oc[(size_t)(j + 2) * d], o3 = oc[(size_t)(j + 3) * d];
+                const float x0 = q[j] - muf[j], x1 = q[j + 1] - muf[j + 1];
+                const float x2 = q[j + 2] - muf[j + 2], x3 = q[j + 3] - muf[j + 3];
+                acc0 = fmaf(o0, x0, acc0); acc1 = fmaf(o1, x1, acc1);
+                acc2 = fmaf(o2, x2, acc2); acc3 = fmaf(o3, x3, acc3);
+            }
+            for (; j < d; ++j) acc0 = fmaf(oc[(size_t)j * d], q[j] - muf[j], acc0);
         }
-        for (; j < d; ++j) acc0 = fmaf(oc[(size_t)j * d], q[j] - muf[j], acc0);
-        acc0 += acc2; acc1 += acc3;
-        cavc[e] = acc0 + acc1;
+        cavc[e] = (acc0 + acc2) + (acc1 + acc3);
     }
 }
 
@@ -561,41 +586,74 @@ __device__ void likelihood_pass_tc(const SamplerArgs& a, unsigned char* smem, un
 // ---------------------------------------------------------------------------
 // per-chain (one warp) helpers
 // ---------------------------------------------------------------------------
-struct ChainCtx {
+// ALLHOT = true (tensor-core kernels): the launch plan guarantees that every hot vector, the cavity term and
+// the cavity mean live in shared memory; they are then addressed through the __shared__ symbol so that the
+// compiler emits ld.shared / st.shared instead of generic loads (which take the L1TEX path: ~50 cycles more
+// per dependent access, and the chain phase is one long dependency chain).
+template <bool ALLHOT>
+struct ChainCtxT {
     const SamplerArgs& a;
     int cg;          // global chain index (k_local*C + c)
     int p, d, J, D, lane;
     uint2 key;
     const float* omega;   // [d*d] fp32 cavity precision
-    const float* muf;     // [d] fp32 cavity mean
+    const float* muf_;    // [d] fp32 cavity mean
     ChainStack* stk;      // shared memory
-    const float* cavc;    // [d] cavity term Omega (phi - mu) of this chain (shared memory)
+    const float* cavc_;   // [d] cavity term Omega (phi - mu) of this chain (shared memory)
     float* hot;           // this chain's block of shared-memory vectors (hot vectors, then hot stack levels)
     float* cold;          // this chain's vectors in global memory
+    uint32_t hot_off, cavc_off, muf_off;      // the same three as byte offsets into dynamic shared memory
     __device__ __forceinline__ float* v(int which) const {
-        if (which < a.hot_nvec) return hot + which * a.P;
-        if (which >= V_STACK && which < V_STACK + 4 * a.hot_levels) return hot + (a.hot_nvec + which - V_STACK) * a.P;
-        return cold + (size_t)which * a.P;
+        if constexpr (ALLHOT) {
+            extern __shared__ __align__(1024) unsigned char smem_dyn[];
+            float* h = reinterpret_cast<float*>(smem_dyn + hot_off);
+            if (which < V_NHOT) return h + which * a.P;
+            if (which >= V_STACK && which < V_STACK + 4 * a.hot_levels) return h + (V_NHOT + which - V_STACK) * a.P;
+            return cold + (size_t)which * a.P;
+        } else {
+            if (which < a.hot_nvec) return hot + which * a.P;
+            if (which >= V_STACK && which < V_STACK + 4 * a.hot_levels) return hot + (a.hot_nvec + which - V_STACK) * a.P;
+            return cold + (size_t)which * a.P;
+        }
+    }
+    __device__ __forceinline__ const float* cavc() const {
+        if constexpr (ALLHOT) {
+            extern __shared__ __align__(1024) unsigned char smem_dyn[];
+            return reinterpret_cast<const float*>(smem_dyn + cavc_off);
+        } else return cavc_;
+    }
+    __device__ __forceinline__ const float* muf() const {
+        if constexpr (ALLHOT) {
+            extern __shared__ __align__(1024) unsigned char smem_dyn[];
+            return reinterpret_cast<const float*>(smem_dyn + muf_off);
+        } else return muf_;
     }
 };
-__device__ __forceinline__ ChainCtx make_chain_ctx(const SamplerArgs& a, const SiteView& sv, int c_local, int p, int d,
-                                                   int J, int D, int lane, uint2 key, const float* om,
-                                                   const float* muf, ChainStack* stk) {
+template <bool ALLHOT>
+__device__ __forceinline__ ChainCtxT<ALLHOT> make_chain_ctx(const SamplerArgs& a, const SiteView& sv, int c_local, int p,
+                                                            int d, int J, int D, int lane, uint2 key, const float* om,
+                                                            const float* muf, ChainStack* stk) {
     const int cg = sv.k * a.C + c_local;
     float* hot = cvec(a, sv, c_local, 0);    // slot 0 of the chain's shared block (when hot_nvec > 0)
     float* cold = a.chain_mem + (size_t)cg * NVEC * a.P;
     const float* cavc = reinterpret_cast<const float*>(sv.sm + a.off_cavc) + (size_t)c_local * d;
-    return ChainCtx{a, cg, p, d, J, D, lane, key, om, muf, stk, cavc, hot, cold};
+    const uint32_t per_chain = (uint32_t)(a.hot_nvec + 4 * a.hot_levels);
+    const uint32_t hot_off = sv.off + (uint32_t)a.off_hot + (uint32_t)c_local * per_chain * (uint32_t)a.P * 4u;
+    const uint32_t cavc_off = sv.off + (uint32_t)a.off_cavc + (uint32_t)(c_local * d) * 4u;
+    const uint32_t muf_off = sv.off + (uint32_t)a.off_omega + (uint32_t)(d * d) * 4u;
+    return ChainCtxT<ALLHOT>{a, cg, p, d, J, D, lane, key, om, muf, stk, cavc, hot, cold, hot_off, cavc_off, muf_off};
 }
 
-__device__ __forceinline__ void vcopy(const ChainCtx& x, int dst, int src) {
+template <class CX>
+__device__ __forceinline__ void vcopy(const CX& x, int dst, int src) {
     float4* D_ = reinterpret_cast<float4*>(x.v(dst));
     const float4* S_ = reinterpret_cast<const float4*>(x.v(src));
     for (int i = x.lane; 4 * i < x.p; i += 32) D_[i] = S_[i];       // vectors are padded to P (multiple of 32)
 }
 
 // kinetic energy 0.5 p' M^-1 p
-__device__ __forceinline__ double kinetic(const ChainCtx& x, const float* p) {
+template <class CX>
+__device__ __forceinline__ double kinetic(const CX& x, const float* p) {
     const float* minv = x.v(V_MINV);
     float s = 0.0f;
     for (int i = x.lane; i < x.p; i += 32) s += minv[i] * p[i] * p[i];
@@ -604,15 +662,16 @@ __device__ __forceinline__ double kinetic(const ChainCtx& x, const float* p) {
 
 // full gradient / potential from the likelihood pass output:
 //   V = -(lp_lik + lp_prior),  g = dV/dq
-__device__ double finish_gradient(const ChainCtx& x, double lp_lik) {
+template <class CX>
+__device__ double finish_gradient(const CX& x, double lp_lik) {
     const float* q = x.v(V_Q);
     const float* gl = x.v(V_GL);
     float* g = x.v(V_G);
     const int d = x.d;
     float quad = 0.0f, sq = 0.0f;
     for (int i = x.lane; i < d; i += 32) {
-        const float ci = x.cavc[i];               // Omega (phi - mu), computed by cavity_term()
-        quad += ci * (q[i] - x.muf[i]);
+        const float ci = x.cavc()[i];               // Omega (phi - mu), computed by cavity_term()
+        quad += ci * (q[i] - x.muf()[i]);
         g[i] = ci - gl[i];
     }
     for (int i = d + x.lane; i < x.p; i += 32) {
@@ -628,7 +687,8 @@ __device__ double finish_gradient(const ChainCtx& x, double lp_lik) {
 // Fused consume step of a tree leaf: gradient/potential from the likelihood pass, second half
 // of the leapfrog, kinetic energy and the leaf's node vectors (rho = p, p_sharp = M^-1 p,
 // proposal = this point) in ONE pass over the parameter vector and ONE round of warp reductions.
-__device__ void leaf_fused(const ChainCtx& x, double lp_lik, float eps_signed, double& Vnew, double& kin) {
+template <class CX>
+__device__ void leaf_fused(const CX& x, double lp_lik, float eps_signed, double& Vnew, double& kin) {
     const float* q = x.v(V_Q);
     const float* gl = x.v(V_GL);
     const float* minv = x.v(V_MINV);
@@ -641,8 +701,8 @@ __device__ void leaf_fused(const ChainCtx& x, double lp_lik, float eps_signed, d
         const float qi = q[i];
         float gi;
         if (i < d) {
-            const float ci = x.cavc[i];
-            prior2 = fmaf(ci, qi - x.muf[i], prior2);
+            const float ci = x.cavc()[i];
+            prior2 = fmaf(ci, qi - x.muf()[i], prior2);
             gi = ci - gl[i];
         } else {
             prior2 = fmaf(qi, qi, prior2);
@@ -667,7 +727,8 @@ __device__ void leaf_fused(const ChainCtx& x, double lp_lik, float eps_signed, d
     kin = 0.5 * b;
 }
 
-__device__ void sample_momentum(const ChainCtx& x, ChainS& s) {
+template <class CX>
+__device__ void sample_momentum(const CX& x, ChainS& s) {
     const float* minv = x.v(V_MINV);
     float* p = x.v(V_P);
     const uint32_t ctr = s.rng++;
@@ -676,7 +737,8 @@ __device__ void sample_momentum(const ChainCtx& x, ChainS& s) {
 }
 
 // first half of a leapfrog step from the working point: p -= e/2 g ; q += e M^-1 p
-__device__ void leapfrog_begin(const ChainCtx& x, float eps_signed) {
+template <class CX>
+__device__ void leapfrog_begin(const CX& x, float eps_signed) {
     float* q = x.v(V_Q); float* p = x.v(V_P); const float* g = x.v(V_G); const float* minv = x.v(V_MINV);
     for (int i = x.lane; i < x.p; i += 32) {
         const float ph = p[i] - 0.5f * eps_signed * g[i];
@@ -685,13 +747,15 @@ __device__ void leapfrog_begin(const ChainCtx& x, float eps_signed) {
     }
     __syncwarp();
 }
-__device__ void leapfrog_end(const ChainCtx& x, float eps_signed) {
+template <class CX>
+__device__ void leapfrog_end(const CX& x, float eps_signed) {
     float* p = x.v(V_P); const float* g = x.v(V_G);
     for (int i = x.lane; i < x.p; i += 32) p[i] -= 0.5f * eps_signed * g[i];
     __syncwarp();
 }
 
-__device__ void begin_ss_trial(const ChainCtx& x, ChainS& s) {
+template <class CX>
+__device__ void begin_ss_trial(const CX& x, ChainS& s) {
     vcopy(x, V_Q, V_QS);
     vcopy(x, V_G, V_GS);
     __syncwarp();
@@ -701,12 +765,14 @@ __device__ void begin_ss_trial(const ChainCtx& x, ChainS& s) {
     s.phase = PH_SS_WAIT;
 }
 
-__device__ void issue_leapfrog(const ChainCtx& x, ChainS& s) {
+template <class CX>
+__device__ void issue_leapfrog(const CX& x, ChainS& s) {
     leapfrog_begin(x, s.sign * s.eps);
     s.phase = PH_TREE_WAIT;
 }
 
-__device__ void begin_subtree(const ChainCtx& x, ChainS& s) {
+template <class CX>
+__device__ void begin_subtree(const CX& x, ChainS& s) {
     const float u = rng_uniform(x.key, s.rng);
     s.sign = (u > 0.5f) ? 1 : -1;
     if (s.sign > 0) { vcopy(x, V_Q, V_QP); vcopy(x, V_P, V_PP); vcopy(x, V_G, V_GP); }
@@ -716,7 +782,8 @@ __device__ void begin_subtree(const ChainCtx& x, ChainS& s) {
     issue_leapfrog(x, s);
 }
 
-__device__ void begin_transition(const ChainCtx& x, ChainS& s) {
+template <class CX>
+__device__ void begin_transition(const CX& x, ChainS& s) {
     vcopy(x, V_Q, V_QS);
     vcopy(x, V_G, V_GS);
     __syncwarp();
@@ -747,7 +814,8 @@ __device__ void next_window(const SamplerArgs& a, ChainS& s) {
 
 // bookkeeping at the end of a transition; returns with the next request issued
 // (or the chain finished)
-__device__ void end_transition(const ChainCtx& x, ChainS& s, int c_local, int k_global_draw_site) {
+template <class CX>
+__device__ void end_transition(const CX& x, ChainS& s, int c_local, int k_global_draw_site) {
     const SamplerArgs& a = x.a;
     const double accept = s.n_leap_tr > 0 ? s.sum_metro / (double)s.n_leap_tr : 0.0;
     s.n_leap_total += s.n_leap_tr;
@@ -836,7 +904,8 @@ __device__ void end_transition(const ChainCtx& x, ChainS& s, int c_local, int k_
 
 // One step of the per-chain state machine: consume the gradient that was just
 // evaluated at V_Q (lp_lik) and advance until the next evaluation is requested.
-__device__ void chain_step(const ChainCtx& x, ChainS& s, double lp_lik, int c_local, int site_draw) {
+template <class CX>
+__device__ void chain_step(const CX& x, ChainS& s, double lp_lik, int c_local, int site_draw) {
     const SamplerArgs& a = x.a;
     if (s.phase == PH_DONE || s.phase == PH_DEAD) return;
     if (s.phase == PH_START_WAIT) {
@@ -1036,11 +1105,13 @@ __device__ __forceinline__ void init_chains(const SamplerArgs& a, const SiteView
 }
 
 // one chain phase of a site: every chain advances to its next gradient request; warp w of nw
+template <bool ALLHOT>
 __device__ __forceinline__ void chain_phase(const SamplerArgs& a, const SiteView& sv, ChainS* cs, ChainStack* cstk,
                                             const double* lp_lik, int* n_active, int p, int J, uint32_t site_seed,
                                             const float* om, const float* muf, int w, int nw, int lane) {
     for (int c = w; c < a.C; c += nw) {
-        ChainCtx x = make_chain_ctx(a, sv, c, p, a.d, J, a.D, lane, make_uint2(site_seed, (uint32_t)c), om, muf, cstk + c);
+        const ChainCtxT<ALLHOT> x = make_chain_ctx<ALLHOT>(a, sv, c, p, a.d, J, a.D, lane,
+                                                           make_uint2(site_seed, (uint32_t)c), om, muf, cstk + c);
         ChainS s = cs[c];                  // private copy: every lane runs the same scalar code
         const int before = s.phase;
         chain_step(x, s, lp_lik[c], c, sv.k);
@@ -1165,7 +1236,7 @@ k_nuts(const SamplerArgs a, const __grid_constant__ CUtensorMap tmap) {
     long long clk_chain = 0, clk_lik = 0, n_ticks = 0;
     for (;;) {
         const long long tk0 = clock64();
-        if (worker) chain_phase(a, sv, cs, cstk, lp_lik, &n_active, p, J, site_seed, om, muf, warp, NWARP, lane);
+        if (worker) chain_phase<USE_TC>(a, sv, cs, cstk, lp_lik, &n_active, p, J, site_seed, om, muf, warp, NWARP, lane);
         __threadfence_block();
         __syncthreads();
         if (n_active <= 0) break;
@@ -1263,8 +1334,8 @@ k_nuts_pp(const SamplerArgs a, const __grid_constant__ CUtensorMap tmap, int n_s
                     chain_group_sync();
                 }
                 const long long t0 = clock64();
-                const SiteView sv{sm, S.k};
-                chain_phase(a, sv, cs, cstk, lp_lik[sc], &S.n_active, S.p, 1, S.seed, om, om + d * d, cw, PP_NCW, lane);
+                const SiteView sv{sm, S.k, (uint32_t)((size_t)sc * a.site_stride)};
+                chain_phase<true>(a, sv, cs, cstk, lp_lik[sc], &S.n_active, S.p, 1, S.seed, om, om + d * d, cw, PP_NCW, lane);
                 __threadfence_block();
                 chain_group_sync();
                 if (ct == 0) { S.clk_chain += clock64() - t0; S.n_ticks += 1; }
@@ -1336,7 +1407,8 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) k_logdensity(const SamplerArg
         likelihood_pass<CP>(a, smem, k_local, k_local, nq, J, row_begin, n_rows, grows, lp_lik, om, muf);
     }
     for (int c = warp; worker && c < nq; c += NWARP) {
-        ChainCtx x = make_chain_ctx(a, SiteView{smem, k_local}, c, p, d, J, D, lane, make_uint2(0u, 0u), om, muf, nullptr);
+        const ChainCtxT<false> x = make_chain_ctx<false>(a, SiteView{smem, k_local}, c, p, d, J, D, lane,
+                                                         make_uint2(0u, 0u), om, muf, nullptr);
         const double V = finish_gradient(x, lp_lik[c]);
         const float* g = x.v(V_G);
         if (lane == 0) lp_out[c] = -V;
@@ -1608,7 +1680,7 @@ int epg_num_params(epg_ctx* c, int k) {
     return c->sites->h_p[k];
 }
 
-static int fill_args(epg_ctx* c, SamplerArgs& a, int C, int CP, int n_sites = 1) {
+static int fill_args(epg_ctx* c, SamplerArgs& a, int C, int CP, int n_sites = 1, bool need_allhot = false) {
     epg_site_data* s = c->sites;
     a.X = s->X; a.y = s->y; a.row0 = s->row0; a.grp_ptr = s->grp_ptr; a.grp_rows = s->grp_rows;
     a.model = s->model; a.D = s->D; a.S = s->S; a.d = c->d;
@@ -1659,6 +1731,12 @@ static int fill_args(epg_ctx* c, SamplerArgs& a, int C, int CP, int n_sites = 1)
     }
     if (const char* e = getenv("EPGPU_NST")) a.tc_nst = atoi(e);
     if (!plan_smem(a, CP, s->max_rows, c->d)) return epg_fail_msg(c, "sampler: shapes exceed the shared-memory plan");
+    if (need_allhot && a.use_tc && !(a.omega_smem && a.hot_nvec >= V_NHOT)) {
+        // the tensor-core kernels address the chain vectors as shared memory: without room for all of them the
+        // fp32 SIMT kernel takes over
+        a.use_tc = 0;
+        if (!plan_smem(a, CP, s->max_rows, c->d)) return epg_fail_msg(c, "sampler: shapes exceed the shared-memory plan");
+    }
     return 0;
 }
 
@@ -1680,7 +1758,7 @@ int epg_tilted_sample(epg_ctx* c, int k0, int k1, const uint32_t* seeds, const e
     if (int rc = epg_reserve_draws(c, n)) return rc;
     SamplerArgs a;
     memset(&a, 0, sizeof(a));
-    if (int rc = fill_args(c, a, C, CP, k1 - k0)) return rc;
+    if (int rc = fill_args(c, a, C, CP, k1 - k0, true)) return rc;
     a.iter = o->iter; a.warmup = warm; a.init_mode = o->init_mode;
     a.max_depth = o->max_treedepth > 0 ? std::min(o->max_treedepth, MAXDEPTH_CAP) : 10;
     a.delta = o->adapt_delta > 0 ? o->adapt_delta : 0.8;
