@@ -177,6 +177,30 @@ def cpu_baseline(model, K, n_k, D, chains, siter, n_sample, procs):
     return its, n_grad / wall, wall
 
 
+def cpu_linalg_baseline(d, n, n_sites=32):
+    """Moment matching + cavity of the oracle (fp64 NumPy/LAPACK restatement of method.py:267-302,413-468)
+    on `n_sites` sites of n draws, one core: microseconds per site."""
+    from oracle import ep_linalg as orc
+    rng = np.random.RandomState(0)
+    Q = np.eye(d) * 3.0
+    r = rng.standard_normal(d)
+    Qi = np.eye(d) * 0.5
+    ri = np.zeros(d)
+    samps = [rng.standard_normal((n, d)) for _ in range(n_sites)]
+    from threadpoolctl import threadpool_limits
+    with threadpool_limits(1):                          # one BLAS thread: these are 50 x 800 problems
+        orc.tilted_moments(samps[0], Q, r, 'sample')   # (library warm-up)
+        orc.cavity(Q, r, Qi, ri)
+        t0 = time.perf_counter()
+        for sm in samps:
+            orc.tilted_moments(sm, Q, r, 'sample')
+        t1 = time.perf_counter()
+        for _ in samps:
+            orc.cavity(Q, r, Qi, ri)
+        t2 = time.perf_counter()
+    return 1e6 * (t1 - t0) / n_sites, 1e6 * (t2 - t1) / n_sites
+
+
 def run_reference(args, model, K, n_k, D, chains, siter):
     """--impl reference: the reference's CPU path for this workload.  PyStan is
     not installable here, so this is the oracle port (kind "port") with one
@@ -365,6 +389,9 @@ def main():
             'sample': 'one chain on each of %d sites (of %d sites x %d chains), one EP iteration, fp64 NumPy '
                       'oracle NUTS, one process per core (%.1f s); scaled to the full workload'
                       % (n_sample, K, chains, cwall)}
+        mom_us, cav_us = cpu_linalg_baseline(d, chains * (siter - siter // 2))
+        line['cpu_baseline']['moments_us_per_site'] = mom_us       # one core; the GPU kernels: profiles/*linalg_timing*
+        line['cpu_baseline']['cavity_us_per_site'] = cav_us
     print(json.dumps(line))
 
 
