@@ -361,7 +361,10 @@ def main():
         'data': 'synthetic',
         'config': {'workload': args.workload, 'model': model + '_sg', 'K': K, 'n_k': n_k, 'D': D, 'd': d,
                    'chains': chains, 'siter': siter, 'parallelism': 'sites sharded %d-way' % world,
-                   'l2': 'inputs larger than L2 (X %.0f MB fp32 per GPU)' % (n_loc * n_k * (D + 3) * 4 / 1e6)},
+                   'l2': ('inputs larger than L2 (X %.0f MB fp32 + bf16 copy per GPU)' if n_loc * n_k * (D + 3) * 4 > 126e6
+                          else 'inputs smaller than L2 (X %.0f MB fp32 per GPU); not flushed: a step re-reads each '
+                               'site\'s X thousands of times by design, the first touch is <0.1 %% of a step')
+                         % (n_loc * n_k * (D + 3) * 4 / 1e6)},
         'grad_evals_per_s': n_leap / max(samp_s, 1e-9),
         'sampling_share': samp_s / (ms_wall * 1e-3),
         'device_ms_per_step': ms_dev / args.steps,
