@@ -2,15 +2,19 @@
 // single-group sites, D+1 <= 64 inputs, <= 16 chains.
 //
 //   per 128-row tile of the site's design matrix (bf16, 64 columns = 128 B rows,
-//   column D holds 1.0, TMA-loaded with the 128-byte swizzle):
-//     GEMM1  F[128 x 16]  = X_tile[128 x 64] . (B_hi + B_lo)'[64 x 16]    (K-major A, M=128)
-//     epilogue (4 warps, one row per thread): tcgen05.ld F -> e = y - sigmoid(f),
-//              lp += y f - softplus(f);  E (bf16) -> shared memory
-//     GEMM2  G[64 x 16] += X_tile'[64 x 128] . E[128 x 16]   (the SAME smem tile read
-//              as an MN-major A operand, M=64, accumulated in TMEM over all tiles)
-//   X is read once per tick from L2/HBM; both contractions run on the tensor
-//   cores; the coefficient matrix is split B = B_hi + B_lo (two bf16 MMAs) so that
-//   the log-density sees fp32-accurate coefficients.
+//   column D holds 1.0, TMA-loaded with the 128-byte swizzle into a ring of 4..8 stages):
+//     GEMM1  F[128 x 32]  = X_tile[128 x 64] . [B_hi | B_lo]'[64 x 32]    (K-major A, M=128, N=32)
+//     epilogue (8 warps = two groups that take alternate tiles, one row per thread):
+//              tcgen05.ld F_hi, F_lo -> e = y - sigmoid(f), lp += y f - softplus(f);
+//              E (bf16) -> shared memory, fence.proxy.async, mbarrier arrive
+//     GEMM2  G[64 x 16] += X_tile'[64 x 128] . E[128 x 16]   (the SAME smem tile read as an
+//              MN-major A operand, accumulated in TMEM over all tiles); issued as 4 instructions
+//              of M=128, N=32, K=16 whose two diagonal accumulator blocks are the products of
+//              two 16-row slices each (see e_off)
+//   X is read once per tick from L2; both contractions run on the tensor cores; the coefficient
+//   matrix is split B = B_hi + B_lo (N dimension of GEMM1) so that the log-density sees
+//   fp32-accurate coefficients.  Per tile the X data crosses shared memory three times (TMA write,
+//   GEMM1 read, GEMM2 read): that bandwidth, not the tensor pipe, bounds the tile phase.
 //
 // Descriptor encodings follow cute/arch/mma_sm100_desc.hpp (SmemDescriptor,
 // InstrDescriptor) and the canonical layouts documented in

@@ -508,7 +508,7 @@ __device__ void likelihood_pass_tc(const SamplerArgs& a, unsigned char* smem, un
                                    const CUtensorMap* tmap, tc::State& st, int k_local, int nchains,
                                    int64_t row_begin, int n_rows, double* lp_out, const float* om, const float* muf) {
     const int tid = threadIdx.x;
-    const bool worker = tid < NTHR;                  // warps 8, 9 only drive TMA / MMA inside the pass
+    const bool worker = tid < NTHR;                  // warps 8, 9, 10 only drive MMA / TMA inside the pass
     const int D = a.D, d = a.d, model = a.model;
     double* lpw = reinterpret_cast<double*>(smem + a.off_lp);       // [NWARP][8]
     const int chain0 = k_local * a.C;
