@@ -85,9 +85,13 @@ void epg_sites_free(epg_ctx* c) {
 
 namespace {
 
-__host__ __device__ inline int model_dphi(int model, int D) { return model == EPG_M4B ? 2 * D + 2 : D + 1; }
+__host__ __device__ inline bool model_four(int model) { return model == EPG_M4B || model == EPG_M5B; }
+__host__ __device__ inline int model_dphi(int model, int D) {
+    return model_four(model) ? 2 * D + 2 : (model == EPG_M2B ? 2 : D + 1);
+}
+// sampled parameters q = [phi (d) | eta (J) | etb]: etb is absent (m1b), one vector per site (m2b) or per group
 __host__ __device__ inline int model_np(int model, int D, int J) {
-    return model_dphi(model, D) + J + (model == EPG_M1B ? 0 : J * D);
+    return model_dphi(model, D) + J + (model == EPG_M1B ? 0 : (model == EPG_M2B ? D : J * D));
 }
 
 __global__ void k_convert_x(const double* __restrict__ src, float* __restrict__ dst, int64_t rows, int D, int S) {
@@ -313,10 +317,16 @@ __device__ void likelihood_pass(const SamplerArgs& a, unsigned char* smem, int s
     const int R = a.R;
     const int S4 = S >> 2;
     const int chain0 = k_local * a.C;
-    const int ia = (model == EPG_M4B) ? 1 : 0;                      // index of log sigma_a in phi
-    const int ib = (model == EPG_M4B) ? 2 + D : 1;                  // start of log sigma_b (m3b/m4b)
+    const bool four = model_four(model);
+    const int ia = four ? 1 : 0;                                    // index of log sigma_a in phi
+    const int ib = four ? 2 + D : 1;                                // start of log sigma_b (m2b: the one scale)
 
     for (int e = tid; e < CP * d; e += NTHR) gphi[e] = 0.0f;
+    if (model == EPG_M2B)                                           // slope gradient accumulates over the groups
+        for (int e = tid; e < nchains * D; e += NTHR) {
+            const int c = e / D, col = e - c * D;
+            cvec(a, SiteView{smem, k_local}, c, V_GL)[d + J + col] = 0.0f;
+        }
     cavity_term(a, smem, om, muf, k_local, nchains, NTHR);
     float lpacc[CP];
 #pragma unroll
@@ -340,12 +350,14 @@ __device__ void likelihood_pass(const SamplerArgs& a, unsigned char* smem, int s
                 const float* q = cvec(a, SiteView{smem, k_local}, c, V_Q);
                 if (col == D) {
                     const float sa = __expf(q[ia]);
-                    v = q[d + j] * sa + (model == EPG_M4B ? q[0] : 0.0f);
+                    v = q[d + j] * sa + (four ? q[0] : 0.0f);
                 } else if (model == EPG_M1B) {
                     v = q[1 + col];
+                } else if (model == EPG_M2B) {
+                    v = q[d + J + col] * __expf(q[ib]);
                 } else {
                     const float etb = q[d + J + j * D + col];
-                    v = etb * __expf(q[ib + col]) + (model == EPG_M4B ? q[2 + col] : 0.0f);
+                    v = etb * __expf(q[ib + col]) + (four ? q[2 + col] : 0.0f);
                 }
             }
             Bm[e] = v;
@@ -466,15 +478,17 @@ __device__ void likelihood_pass(const SamplerArgs& a, unsigned char* smem, int s
                 const float eta = q[d + j];
                 gl[d + j] = sa * gsum;
                 gphi[c * d + ia] += sa * eta * gsum;      // (c, col) pairs own distinct slots
-                if (model == EPG_M4B) gphi[c * d + 0] += gsum;
+                if (four) gphi[c * d + 0] += gsum;
             } else if (model == EPG_M1B) {
                 gphi[c * d + 1 + col] += gsum;
+            } else if (model == EPG_M2B) {
+                gl[d + J + col] += __expf(q[ib]) * gsum;  // d/d etb = sigma_b sum_j g_j (log sigma_b: below)
             } else {
                 const float sb = __expf(q[ib + col]);
                 const float etb = q[d + J + j * D + col];
                 gl[d + J + j * D + col] = sb * gsum;
                 gphi[c * d + ib + col] += sb * etb * gsum;
-                if (model == EPG_M4B) gphi[c * d + 2 + col] += gsum;
+                if (four) gphi[c * d + 2 + col] += gsum;
             }
         }
     }
@@ -489,7 +503,16 @@ __device__ void likelihood_pass(const SamplerArgs& a, unsigned char* smem, int s
         double s = 0.0;
         for (int w = 0; w < NWARP; ++w) s += lpw[w * CP + tid];
         lp_out[tid] = s;
+        if (model == EPG_M2B) {
+            // d/d log sigma_b = sum_i etb_i (sigma_b g_i), in a fixed order
+            const float* q = cvec(a, SiteView{smem, k_local}, tid, V_Q);
+            const float* gl = cvec(a, SiteView{smem, k_local}, tid, V_GL);
+            float acc = 0.0f;
+            for (int col = 0; col < D; ++col) acc = fmaf(q[d + J + col], gl[d + J + col], acc);
+            gphi[tid * d + ib] = acc;
+        }
     }
+    __syncthreads();
     for (int e = tid; e < CP * d; e += NTHR) {
         const int c = e / d, i = e - c * d;
         if (c < nchains) cvec(a, SiteView{smem, k_local}, c, V_GL)[i] = gphi[e];
@@ -512,8 +535,9 @@ __device__ void likelihood_pass_tc(const SamplerArgs& a, unsigned char* smem, un
     const int D = a.D, d = a.d, model = a.model;
     double* lpw = reinterpret_cast<double*>(smem + a.off_lp);       // [NWARP][8]
     const int chain0 = k_local * a.C;
-    const int ia = (model == EPG_M4B) ? 1 : 0;
-    const int ib = (model == EPG_M4B) ? 2 + D : 1;
+    const bool four = model_four(model);
+    const int ia = four ? 1 : 0;
+    const int ib = four ? 2 + D : 1;
     PROF_T(q0);
     if (worker) {
         // coefficient operands B = B_hi + B_lo (bf16 each), K-major interleaved layout
@@ -522,9 +546,10 @@ __device__ void likelihood_pass_tc(const SamplerArgs& a, unsigned char* smem, un
             float v = 0.0f;
             if (col <= D) {
                 const float* q = cvec(a, SiteView{smem, k_local}, c, V_Q);
-                if (col == D) v = q[d] * __expf(q[ia]) + (model == EPG_M4B ? q[0] : 0.0f);
+                if (col == D) v = q[d] * __expf(q[ia]) + (four ? q[0] : 0.0f);
                 else if (model == EPG_M1B) v = q[1 + col];
-                else v = q[d + 1 + col] * __expf(q[ib + col]) + (model == EPG_M4B ? q[2 + col] : 0.0f);
+                else if (model == EPG_M2B) v = q[d + 1 + col] * __expf(q[ib]);
+                else v = q[d + 1 + col] * __expf(q[ib + col]) + (four ? q[2 + col] : 0.0f);
             }
             const __nv_bfloat16 hi = __float2bfloat16(v);
             const __nv_bfloat16 lo = __float2bfloat16(v - __bfloat162float(hi));
@@ -559,21 +584,33 @@ __device__ void likelihood_pass_tc(const SamplerArgs& a, unsigned char* smem, un
                 const float sa = __expf(q[ia]);
                 gl[d] = sa * gsum;
                 gl[ia] = sa * q[d] * gsum;
-                if (model == EPG_M4B) gl[0] = gsum;
+                if (four) gl[0] = gsum;
             } else if (model == EPG_M1B) {
                 gl[1 + col] = gsum;
+            } else if (model == EPG_M2B) {
+                gl[d + 1 + col] = __expf(q[ib]) * gsum;       // (log sigma_b: below, one thread per chain)
             } else {
                 const float sb = __expf(q[ib + col]);
                 const float etb = q[d + 1 + col];
                 gl[d + 1 + col] = sb * gsum;
                 gl[ib + col] = sb * etb * gsum;
-                if (model == EPG_M4B) gl[2 + col] = gsum;
+                if (four) gl[2 + col] = gsum;
             }
         }
         if (tid < nchains) {
             double sum = 0.0;
             for (int w = 0; w < NWARP; ++w) sum += lpw[w * tc::NCH + tc::chain_col(tid)];
             lp_out[tid] = sum;
+            if (model == EPG_M2B) {
+                // d/d log sigma_b = sigma_b sum_i etb_i g_i, in a fixed order
+                const float* gout = reinterpret_cast<const float*>(tcb + tc::Smem::GOUT);
+                const float* q = cvec(a, SiteView{smem, k_local}, tid, V_Q);
+                float acc = 0.0f;
+                for (int col = 0; col < D; ++col)
+                    acc = fmaf(q[d + 1 + col], gout[tc::chain_col(tid) * tc::KW + col] +
+                                                   gout[(tc::NCH + tc::chain_col(tid)) * tc::KW + col], acc);
+                cvec(a, SiteView{smem, k_local}, tid, V_GL)[ib] = __expf(q[ib]) * acc;
+            }
         }
     }
     lik_group_sync();
@@ -674,10 +711,11 @@ __device__ double finish_gradient(const CX& x, double lp_lik) {
         quad += ci * (q[i] - x.muf()[i]);
         g[i] = ci - gl[i];
     }
+    const bool laplace = x.a.model == EPG_M5B;        // eta, etb ~ double_exponential(0,1): -|q| instead of -q^2/2
     for (int i = d + x.lane; i < x.p; i += 32) {
         const float qi = q[i];
-        sq += qi * qi;
-        g[i] = qi - gl[i];
+        sq += laplace ? 2.0f * fabsf(qi) : qi * qi;
+        g[i] = (laplace ? copysignf(qi != 0.0f ? 1.0f : 0.0f, qi) : qi) - gl[i];
     }
     const double prior = -0.5 * warp_sum((double)quad) - 0.5 * warp_sum((double)sq);
     __syncwarp();
@@ -696,6 +734,7 @@ __device__ void leaf_fused(const CX& x, double lp_lik, float eps_signed, double&
     float* crho = x.v(V_CRHO); float* cpsl = x.v(V_CPSL);
     float* qp_ = x.v(V_QPROP); float* gp_ = x.v(V_GPROP);
     const int d = x.d;
+    const bool laplace = x.a.model == EPG_M5B;
     float prior2 = 0.0f, kin2 = 0.0f;                 // (phi-mu)'Omega(phi-mu) + |latents|^2 ;  p'M^-1 p
     for (int i = x.lane; i < x.p; i += 32) {
         const float qi = q[i];
@@ -704,6 +743,9 @@ __device__ void leaf_fused(const CX& x, double lp_lik, float eps_signed, double&
             const float ci = x.cavc()[i];
             prior2 = fmaf(ci, qi - x.muf()[i], prior2);
             gi = ci - gl[i];
+        } else if (laplace) {
+            prior2 += 2.0f * fabsf(qi);
+            gi = copysignf(qi != 0.0f ? 1.0f : 0.0f, qi) - gl[i];
         } else {
             prior2 = fmaf(qi, qi, prior2);
             gi = qi - gl[i];
@@ -1551,7 +1593,8 @@ extern "C" {
 int epg_upload_sites(epg_ctx* c, int model, int D, const int64_t* k_lim, const double* X, const int64_t* y,
                      const int32_t* j_ind, const int32_t* Jk) {
     if (!c->arr[EPG_Q]) return epg_fail_msg(c, "epg_upload_sites: call epg_init_state first");
-    if (model != EPG_M1B && model != EPG_M3B && model != EPG_M4B) return epg_fail_msg(c, "unknown model id");
+    if (model != EPG_M1B && model != EPG_M2B && model != EPG_M3B && model != EPG_M4B && model != EPG_M5B)
+        return epg_fail_msg(c, "unknown model id");
     if (D < 1 || D > 1000) return epg_fail_msg(c, "bad D");
     if (model_dphi(model, D) != c->d) return epg_fail_msg(c, "dphi of the model does not match the state dimension");
     if ((j_ind == nullptr) != (Jk == nullptr)) return epg_fail_msg(c, "j_ind and Jk must be given together");

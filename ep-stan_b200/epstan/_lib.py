@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(os.path.dirname(_HERE), 'libepgpu.so')
 
 # enum epg_array
 (Q, R, Q0, R0, QI, RI, QI2, RI2, DQI, DRI, CAVQ, CAVM, S, M, PARTIAL, TMEAN) = range(16)
-MODEL_IDS = {'m1b': 1, 'm3b': 3, 'm4b': 4}
+MODEL_IDS = {'m1b': 1, 'm2b': 2, 'm3b': 3, 'm4b': 4, 'm5b': 5}
 PREC_ESTIM = {'sample': 0, 'olse': 1}
 
 _c_double_p = C.POINTER(C.c_double)

@@ -78,7 +78,7 @@ class Worker(object):
     method.py:121-475; same constructor, ``cavity`` and ``tilted``).
 
     ``stan_model`` may be a model path / name string (its base name selects a
-    built-in CUDA density: m1b, m3b, m4b and their ``_sg`` variants), a
+    built-in CUDA density: m1b, m2b, m3b, m4b, m5b and their ``_sg`` variants), a
     ``util.BuiltinModel``, or any object with a PyStan-2 style
     ``sampling(data=, chains=, iter=, warmup=, thin=, init=, seed=, refresh=)``
     method, in which case its draws are moment-matched on the GPU.

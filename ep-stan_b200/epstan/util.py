@@ -183,7 +183,7 @@ def get_last_fit_sample(fit, out=None):
 # host-side helpers
 # ---------------------------------------------------------------------------
 
-BUILTIN_MODELS = ('m1b', 'm3b', 'm4b')
+BUILTIN_MODELS = ('m1b', 'm2b', 'm3b', 'm4b', 'm5b')
 
 
 class BuiltinModel(object):
@@ -204,7 +204,7 @@ class BuiltinModel(object):
         self.model_id = _lib.MODEL_IDS[base]
 
     def dphi(self, D):
-        return {'m1b': D + 1, 'm3b': D + 1, 'm4b': 2 * D + 2}[self.family]
+        return {'m1b': D + 1, 'm2b': 2, 'm3b': D + 1, 'm4b': 2 * D + 2, 'm5b': 2 * D + 2}[self.family]
 
     def __repr__(self):
         return "BuiltinModel('{}')".format(self.name)

@@ -7,7 +7,7 @@ Execute with:
 Same command line as the reference (fit.py:972-1004): all 26 option names of
 CONFS with the defaults of CONF_DEFAULT, e.g.
     $ python fit.py m1b --run_ep 1 --K 4
-Group ``<model_name>`` is a simulated model in ./models (m1b, m3b, m4b).  The
+Group ``<model_name>`` is a simulated model in ./models (m1b, m2b, m3b, m4b, m5b).  The
 EP branch (``--run_ep``) is the reference's (fit.py:279-459) on the GPU Master.
 ``--run_full`` / ``--run_target`` sample the full-data posterior with the same
 built-in NUTS sampler (one site holding every group, cavity = prior);

@@ -1,8 +1,8 @@
-"""Hierarchical logistic-regression simulators behind m1b / m3b / m4b.
+"""Hierarchical logistic-regression simulators behind m1b / m2b / m3b / m4b / m5b.
 
 One table-driven implementation; the RNG call order follows the reference's
-simulators (experiment/models/m1b.py:83-176, m3b.py, m4b.py:95-195) so that the
-same `seed_data` gives the same data set.
+simulators (experiment/models/m1b.py:83-176, m2b.py:95-176, m3b.py, m4b.py:95-195,
+m5b.py:98-200) so that the same `seed_data` gives the same data set.
 """
 
 import numpy as np
@@ -15,8 +15,10 @@ B_ABS_MIN_SUM = 1e-4     # keep |sum(beta)| away from zero (mean shifts divide b
 SPEC = {
     # prior variances are those of the reference modules (m1b.py:46-51, m3b.py:45-50, m4b.py:45-59)
     'm1b': dict(dphi=lambda D: D + 1, group_slopes=False),
+    'm2b': dict(dphi=lambda D: 2, group_slopes=False),
     'm3b': dict(dphi=lambda D: D + 1, group_slopes=True),
     'm4b': dict(dphi=lambda D: 2 * D + 2, group_slopes=True),
+    'm5b': dict(dphi=lambda D: 2 * D + 2, group_slopes=True),
 }
 
 
@@ -41,6 +43,18 @@ class HierLogistic(object):
                 s += beta[i]
             alpha_j = rng.randn(J) * sigma_a
             return alpha_j, beta, np.append(np.log(sigma_a), beta), beta
+        if fam == 'm2b':
+            # one slope vector for all groups, scaled by a single sigma_b (intercepts first, then slopes)
+            sigma_a, sigma_b = 1.0, 1.0
+            alpha_j = rng.randn(J) * sigma_a
+            beta = rng.randn(D) * sigma_b
+            s = beta.sum()
+            while abs(s) < B_ABS_MIN_SUM:
+                i = rng.randint(D)
+                s -= beta[i]
+                beta[i] = rng.randn() * sigma_b
+                s += beta[i]
+            return alpha_j, beta, np.array([np.log(sigma_a), np.log(sigma_b)]), beta
         if fam == 'm3b':
             sigma_a = 1.0
             sigma_b = np.exp(rng.randn(D) * 1.0)
@@ -48,6 +62,15 @@ class HierLogistic(object):
             beta_j = rng.randn(J, D) * sigma_b
             scale = sigma_b
             phi = np.append(np.log(sigma_a), np.log(sigma_b))
+        elif fam == 'm5b':
+            # heavy-tailed truth: half-Cauchy scales, Laplace locations and latents
+            mu_a, sigma_a = 0.1, 1.0
+            sigma_b = np.abs(rng.standard_cauchy(D) * 1.0)
+            mu_b = rng.laplace(size=D) * 0.0
+            alpha_j = mu_a + rng.laplace(size=J) * sigma_a
+            beta_j = mu_b + rng.laplace(size=(J, D)) * sigma_b
+            scale = sigma_b
+            phi = np.concatenate(([mu_a, np.log(sigma_a)], mu_b, np.log(sigma_b)))
         else:
             mu_a, sigma_a = 1.5, np.exp(0.4)
             mu_b = rng.rand(D) * 4.0 - 2.0
@@ -105,12 +128,12 @@ class HierLogistic(object):
         if self.family == 'm4b':
             var = np.concatenate(([4.0 ** 2, 2.0 ** 2], np.full(D, 4.0 ** 2), np.full(D, 2.0 ** 2)))
         else:
-            var = np.full(D + 1, 1.5 ** 2)
+            var = np.full(self.dphi, 1.5 ** 2)
         m0 = np.zeros(self.dphi)
         return np.diag(var).T, m0, np.diag(1.0 / var).T, m0 / var
 
     def get_param_definitions(self):
         """names, shapes, hierarchical-dimension index of the inferred parameters."""
-        if self.family == 'm1b':
+        if self.family in ('m1b', 'm2b'):
             return ('alpha', 'beta'), ((self.J,), (self.D,)), (0, None)
         return ('alpha', 'beta'), ((self.J,), (self.J, self.D)), (0, 0)

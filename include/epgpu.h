@@ -60,8 +60,10 @@ enum epg_array {
 /* ---- tilted log-density families (experiment/models/<name>[_sg].stan) ---- */
 enum epg_model {
     EPG_M1B = 1,    /* m1b.stan:21-42, m1b_sg.stan:19-35: phi=[log sigma_a, beta]           */
+    EPG_M2B = 2,    /* m2b.stan:21-46, m2b_sg.stan:19-38: phi=[log sigma_a, log sigma_b], one slope vector etb(D) per site */
     EPG_M3B = 3,    /* m3b.stan:21-49, m3b_sg.stan:19-39: phi=[log sigma_a, log sigma_b]    */
-    EPG_M4B = 4     /* m4b.stan:21-53, m4b_sg.stan:19-43: phi=[mu_a,log sigma_a,mu_b,log sigma_b] */
+    EPG_M4B = 4,    /* m4b.stan:21-53, m4b_sg.stan:19-43: phi=[mu_a,log sigma_a,mu_b,log sigma_b] */
+    EPG_M5B = 5     /* m5b.stan:21-53, m5b_sg.stan:19-45: m4b with double_exponential(0,1) latents */
 };
 
 enum epg_prec_estim { EPG_PREC_SAMPLE = 0, EPG_PREC_OLSE = 1 };  /* method.py:163 */

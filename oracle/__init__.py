@@ -13,7 +13,7 @@ ep_linalg.py   fp64 NumPy/SciPy restatement of the moment-matching / cavity /
                (imported in the build container) by tests/golden/*.npz, see
                make_golden.py.
 density.py     fp64 NumPy restatement of the tilted log-densities and gradients
-               of experiment/models/m{1,3,4}b[_sg].stan.  Pinned by finite
+               of experiment/models/m{1,2,3,4,5}b[_sg].stan.  Pinned by finite
                differences only (Stan itself is not available) -> the sampling
                half is "parity unpinned".
 nuts.py        fp64 NumPy restatement of Stan 2.17's adaptive diag_e NUTS

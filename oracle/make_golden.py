@@ -229,9 +229,9 @@ def gen_misc(ep, out):
 
 
 def gen_models(ep, out):
-    """experiment/models/m{1,3,4}b.py simulators and priors (small shapes)."""
+    """experiment/models/m{1..5}b.py simulators and priors (small shapes)."""
     import importlib
-    for name in ('m1b', 'm3b', 'm4b'):
+    for name in ('m1b', 'm2b', 'm3b', 'm4b', 'm5b'):
         mod = importlib.import_module('models.' + name)
         for tag, kw, npg in (('corr', dict(Sigma_x='rand'), 5), ('iid', dict(), [3, 8])):
             mdl = mod.model(6, 3, npg)

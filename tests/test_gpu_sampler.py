@@ -98,7 +98,8 @@ def _moment_check(draws_gpu, per_chain_gpu, ref):
 
 
 @pytest.mark.parametrize('model,J,n,D,C', [('m1b', 1, 300, 4, 8), ('m3b', 1, 400, 3, 8),
-                                           ('m4b', 2, 300, 3, 4), ('m1b', 5, 250, 6, 16)])
+                                           ('m4b', 2, 300, 3, 4), ('m1b', 5, 250, 6, 16),
+                                           ('m2b', 3, 300, 4, 8), ('m5b', 1, 300, 3, 8)])
 def test_sampler_vs_oracle_nuts(model, J, n, D, C):
     site = synth.make_site(model, n, D, J, seed=21)
     NS = 6

@@ -21,7 +21,7 @@ def test_model_simulators_match_reference(golden):
         sys.path.insert(0, EXP)
     import importlib
     g = golden['models']
-    for name in ('m1b', 'm3b', 'm4b'):
+    for name in ('m1b', 'm2b', 'm3b', 'm4b', 'm5b'):
         mod = importlib.import_module('models.' + name)
         for tag, kw, npg in (('corr', dict(Sigma_x='rand'), 5), ('iid', dict(), [3, 8])):
             dat = mod.model(6, 3, npg).simulate_data(rng=100, **kw)
