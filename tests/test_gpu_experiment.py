@@ -28,14 +28,14 @@ def test_fit_cli_options(fit):
     assert abs(fit.default_df0(32)(1) - 0.5) < 1e-15 and fit.EP_DEFAULT_ITERS_TO_RUN(4) == 20
 
 
-@pytest.mark.parametrize('model,K', [('m1b', 4), ('m4b', 8), ('m3b', 2)])
+@pytest.mark.parametrize('model,K', [('m1b', 4), ('m4b', 8), ('m3b', 2), ('m2b', 4), ('m5b', 8)])
 def test_fit_main_ep(fit, tmp_path, monkeypatch, model, K):
     """K < J (grouped sites, `<model>.stan` density) and K == J (`_sg` density)."""
     monkeypatch.setattr(fit, 'RES_PATH', str(tmp_path))
     conf = fit.configurations(J=8, D=3, K=K, npg=25, run_ep=True, iter=3, siter=100, chains=4)
     fit.main(model, conf)
     res = np.load(os.path.join(str(tmp_path), 'res_d_%s.npz' % model), allow_pickle=True)
-    d = {'m1b': 4, 'm3b': 4, 'm4b': 8}[model]
+    d = {'m1b': 4, 'm2b': 2, 'm3b': 4, 'm4b': 8, 'm5b': 8}[model]
     assert res['m_s_ep'].shape == (4, d) and res['S_s_ep'].shape == (4, d, d)
     assert res['time_s_ep'].shape == (4,) and np.isnan(res['mrhat_s_ep'][0])
     assert np.all(np.isfinite(res['m_s_ep'])) and np.all(np.diff(res['time_s_ep']) > 0)
