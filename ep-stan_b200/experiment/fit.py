@@ -11,7 +11,7 @@ Group ``<model_name>`` is a simulated model in ./models (m1b, m2b, m3b, m4b, m5b
 EP branch (``--run_ep``) is the reference's (fit.py:279-459) on the GPU Master.
 ``--run_full`` / ``--run_target`` sample the full-data posterior with the same
 built-in NUTS sampler (one site holding every group, cavity = prior);
-``--run_consensus`` and ``--mix`` are outside the EP path and not provided.
+``--mix`` is outside the EP path and not provided; ``--run_consensus`` pools per-site draws on one GPU.
 
 Results go to ./results with the reference's file names and npz keys
 (res_d_<model>.npz: m_s_ep, S_s_ep, time_s_ep, mstepsize_s_ep, mrhat_s_ep;
@@ -54,6 +54,7 @@ CONF_DEFAULT = dict(
 )
 
 FULL_ITERS = [50, 100, 200, 300, 400, 600, 800, 1000, 1200, 1600, 2000, 3200]
+CONS_ITERS = [50, 100, 500, 1000, 2000, 4000]
 
 
 def EP_DEFAULT_ITERS_TO_RUN(K):
@@ -119,6 +120,59 @@ def _full_posterior_draws(model_name, data, prior, chains, siter, seed):
     return w.saved_samp['phi'], w
 
 
+def _site_master(model_name, data, J, K, options):
+    """Master over K sites built from the J simulated groups (reference fit.py:300-345)."""
+    if K < 2:
+        raise ValueError("K should be at least 2.")
+    elif K < J:
+        Nk, Nj_k, j_ind_k = distribute_groups(J, K, data.Nj)
+        return Master(os.path.join(MOD_PATH, model_name), data.X, data.y,
+                      A_k={'J': Nj_k}, A_n={'j_ind': j_ind_k + 1}, site_sizes=Nk, **options)
+    elif K == J:
+        return Master(os.path.join(MOD_PATH, model_name + '_sg'), data.X, data.y,
+                      site_sizes=data.Nj, **options)
+    elif K <= data.N:
+        raise NotImplementedError("Splitting the groups not implemented.")
+    raise ValueError("K cant be greater than number of samples")
+
+
+def _consensus_mc(model_name, data, prior, J, K, conf, iters_list):
+    """Consensus MC baseline (reference fit.py:539-675): every site is sampled on its own against
+    the fractionated prior N(Q0/K, r0/K) and the draws of all sites are pooled.  The sites are the
+    ones of the EP run, so the batched GPU sampler is used as is: the 'cavity' of every site is set
+    to the fractionated prior."""
+    from scipy import linalg
+    from epstan import _lib
+    from epstan.method import MAX_UINT
+    master = _site_master(model_name, data, J, K, dict(prior=prior, chains=conf.chains, iter=conf.siter))
+    sh = master._shard
+    if sh.comm.size > 1:
+        raise NotImplementedError("consensus MC runs on one GPU (it pools the draws of all sites)")
+    ctx, d = sh.ctx, master.dphi
+    Qk, rk = prior['Q'] / K, prior['r'] / K
+    mk = linalg.cho_solve(linalg.cho_factor(Qk), rk)
+    ctx.upload(_lib.CAVQ, np.asfortranarray(np.repeat(Qk[:, :, None], K, axis=2)))
+    ctx.upload(_lib.CAVM, np.asfortranarray(np.repeat(mk[:, None], K, axis=1)))
+    seeds = np.random.RandomState(seed=conf.seed_cons).randint(0, MAX_UINT, size=K)   # constant over the runs
+    n_it = len(iters_list)
+    out = dict(m_s_cons=np.full((n_it, d), np.nan), S_s_cons=np.full((n_it, d, d), np.nan),
+               time_s_cons=np.full(n_it, np.nan), mstepsize_s_cons=np.full(n_it, np.nan),
+               mrhat_s_cons=np.full(n_it, np.nan))
+    for i, iters in enumerate(iters_list):
+        iters = int(iters)
+        print('  iter {}: {}'.format(i + 1, iters))
+        msteps, mrhat, _, secs = ctx.tilted_sample(seeds, conf.chains, iters)
+        n = conf.chains * (iters - iters // 2)
+        samp = ctx.get_draws(n).transpose(0, 2, 1).reshape(-1, d)        # all sites' draws of phi
+        out['m_s_cons'][i] = samp.mean(axis=0)
+        samp = samp - out['m_s_cons'][i]
+        out['S_s_cons'][i] = samp.T.dot(samp) / (samp.shape[0] - 1)
+        out['time_s_cons'][i] = secs
+        out['mstepsize_s_cons'][i] = np.mean(msteps)
+        out['mrhat_s_cons'][i] = np.max(mrhat)
+    return out
+
+
 def main(model_name, conf, ret_master=False):
     """Fit requested model with given configurations (reference fit.py:210-760).
     ``ret_master`` returns the epstan Master before running it."""
@@ -152,20 +206,7 @@ def main(model_name, conf, ret_master=False):
             raise NotImplementedError("--mix feeds Master.mix_pred, which is outside the EP path")
         epstan_options = dict(prior=prior, prec_estim=conf.prec_estim, df0=df0, init_site=None,
                               chains=conf.chains, iter=conf.siter, warmup=None, thin=1)
-        if K < 2:
-            raise ValueError("K should be at least 2.")
-        elif K < J:
-            Nk, Nj_k, j_ind_k = distribute_groups(J, K, data.Nj)
-            epstan_master = Master(os.path.join(MOD_PATH, model_name), data.X, data.y,
-                                   A_k={'J': Nj_k}, A_n={'j_ind': j_ind_k + 1}, site_sizes=Nk,
-                                   **epstan_options)
-        elif K == J:
-            epstan_master = Master(os.path.join(MOD_PATH, model_name + '_sg'), data.X, data.y,
-                                   site_sizes=data.Nj, **epstan_options)
-        elif K <= data.N:
-            raise NotImplementedError("Splitting the groups not implemented.")
-        else:
-            raise ValueError("K cant be greater than number of samples")
+        epstan_master = _site_master(model_name, data, J, K, epstan_options)
         if ret_master:
             print("Returning epstan.Master")
             return epstan_master
@@ -207,8 +248,15 @@ def main(model_name, conf, ret_master=False):
                      S_s_full=np.array(S_s), time_s_full=np.array(t_s))
             print("Full model results saved.")
 
-    if conf.run_consensus or (conf.run_all and False):
-        raise NotImplementedError("consensus MC is a competitor baseline outside the EP path (SURVEY 2.1 #8)")
+    # --------------------------------------------------------------- consensus MC
+    if conf.run_consensus or conf.run_all:
+        print("Consensus MC")
+        iters_list = list(CONS_ITERS) + ([CONS_ITERS[-1] * 1.7] if K == J else [])   # "run additionally a bit longer"
+        res_c = _consensus_mc(model_name, data, prior, J, K, conf, iters_list)
+        if conf.save_res:
+            np.savez(_res_file('res_c', model_name, conf), conf=conf.__dict__, **res_c)
+            print("Consensus MC results saved.")
+        print("Done with consensus MC")
 
     # --------------------------------------------------------- target approximation
     if conf.run_target or conf.run_all:
@@ -271,7 +319,7 @@ CONF_HELP = dict(
     J='number of hierarchical groups', D='number of inputs', K='number of sites',
     npg='number of observations per group (constant or min max)', cor_input='correlated input variable',
     run_all='run all the methods', run_ep='run the distributed EP method', run_full='run the full model method',
-    run_consensus='run consensus MC method (not provided)', run_target='run target approximation',
+    run_consensus='run consensus MC method', run_target='run target approximation',
     iter='number of distributed EP iterations', siter='sampler iterations in each major iteration',
     target_siter='sampler iterations for the target approximation', chains='number of chains used in sampling',
     damp='damping factor constant', mix='mix last iteration samples (not provided)',

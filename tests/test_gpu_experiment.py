@@ -57,3 +57,20 @@ def test_target_and_find_damp(fit, tmp_path, monkeypatch):
     assert np.all(np.isfinite(out['kls_selected'])) and np.all(np.isfinite(out['damps_selected']))
     # EP moves the approximation towards the full-data target
     assert out['kls_selected'][-1] < out['kls_selected'][0]
+
+
+@pytest.mark.parametrize('K', [6, 3])
+def test_fit_consensus_mc(fit, tmp_path, monkeypatch, K):
+    """fit.py --run_consensus (reference fit.py:539-675): per-site sampling against the fractionated
+    prior, pooled moments, `res_c_*.npz` schema; K == J appends the longer run."""
+    monkeypatch.setattr(fit, 'RES_PATH', str(tmp_path))
+    monkeypatch.setattr(fit, 'CONS_ITERS', [40, 80])
+    conf = fit.configurations(J=6, D=2, K=K, npg=30, run_consensus=True, chains=4)
+    fit.main('m1b', conf)
+    res = np.load(os.path.join(str(tmp_path), 'res_c_m1b.npz'), allow_pickle=True)
+    n_it = 3 if K == 6 else 2
+    assert res['m_s_cons'].shape == (n_it, 3) and res['S_s_cons'].shape == (n_it, 3, 3)
+    assert np.all(np.isfinite(res['m_s_cons'])) and np.all(res['time_s_cons'] > 0)
+    assert np.all(res['mstepsize_s_cons'] > 0) and np.all(res['mrhat_s_cons'] > 0.9)
+    for S in res['S_s_cons']:
+        assert np.all(np.linalg.eigvalsh(S) > 0)
