@@ -210,12 +210,23 @@ def run_reference(args, model, K, n_k, D, chains, siter):
         return
     cores = os.cpu_count() or 1
     n_sample = min(K, max(cores, 2))
+    # Bounded sample: a step = ONE chain on each of n_sample sites; the warm-up steps (siter/4 iterations)
+    # also calibrate the cost per sampling iteration, and when --steps full-length steps would not fit in
+    # REF_BUDGET_S the timed steps run fewer iterations per chain and are scaled to `siter`.
+    REF_BUDGET_S = 240.0
+    t_begin = time.perf_counter()
+    siter_w = max(20, siter // 4)
+    wall_w = None
+    for i in range(max(args.warmup, 1)):
+        _, _, wall_w = cpu_baseline(model, K, n_k, D, chains, siter_w, n_sample, cores)
+    per_iter = wall_w / siter_w
+    remaining = max(REF_BUDGET_S - (time.perf_counter() - t_begin), 30.0)
+    siter_step = siter if per_iter * siter * args.steps <= remaining else \
+        max(20, min(siter, int(remaining / (args.steps * per_iter))))
     vals = []
-    for i in range(args.warmup + args.steps):
-        its, gps, wall = cpu_baseline(model, K, n_k, D, chains, max(20, siter // 4) if i < args.warmup else siter,
-                                      n_sample, cores)
-        if i >= args.warmup:
-            vals.append((its, gps, wall))
+    for i in range(args.steps):
+        its, gps, wall = cpu_baseline(model, K, n_k, D, chains, siter_step, n_sample, cores)
+        vals.append((its * siter_step / float(siter), gps, wall))
     its = float(np.mean([v[0] for v in vals]))
     line = {
         'impl': 'reference', 'metric': 'EP iterations/sec (K sites, all draws)', 'value': its,
@@ -226,8 +237,9 @@ def run_reference(args, model, K, n_k, D, chains, siter):
                    'chains': chains, 'siter': siter},
         'grad_evals_per_s': float(np.mean([v[1] for v in vals])),
         'cpu_baseline': {'value': its, 'unit': 'it/s', 'cores': cores, 'kind': 'port',
-                         'sample': 'one chain on each of %d sites per step (of %d sites x %d chains), fp64 NumPy '
-                                   'oracle NUTS, one process per core; scaled to the full workload' % (n_sample, K, chains)},
+                         'sample': 'one chain of %d (of %d) iterations on each of %d sites per step (of %d sites x %d '
+                                   'chains), fp64 NumPy oracle NUTS, one process per core; scaled to the full workload'
+                                   % (siter_step, siter, n_sample, K, chains)},
         'e2e': {'value': its, 'unit': 'it/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }
     print(json.dumps(line))
