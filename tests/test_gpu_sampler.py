@@ -16,6 +16,7 @@ from oracle import density as dens
 from oracle import ep_linalg as orc
 from oracle import nuts
 import synth
+import oracle_refs
 
 pytestmark = pytest.mark.gpu
 
@@ -81,19 +82,16 @@ def test_logdensity_parity_tensor_core(model, n, D):
 
 
 def _moment_check(draws_gpu, per_chain_gpu, ref):
-    """4 x MCSE agreement of means; variances within 4 x their MC error."""
-    _, mcse_g = nuts.ess_mcse(per_chain_gpu)
-    _, mcse_r = nuts.ess_mcse(ref['per_chain'])
-    tol = 4.0 * np.sqrt(mcse_g ** 2 + mcse_r ** 2)
-    dm = np.abs(draws_gpu.mean(axis=0) - ref['draws'].mean(axis=0))
+    """4 x MCSE agreement of means; variances within 4 x their MC error.  `ref`: summary of the
+    oracle run (mean, var, ess, mcse of phi; tests/oracle_refs.py)."""
+    ess_g, mcse_g = nuts.ess_mcse(per_chain_gpu)
+    tol = 4.0 * np.sqrt(mcse_g ** 2 + ref['mcse'] ** 2)
+    dm = np.abs(draws_gpu.mean(axis=0) - ref['mean'])
     assert np.all(dm < tol), (dm / tol).max()
     vg = draws_gpu.var(axis=0, ddof=1)
-    vr = ref['draws'].var(axis=0, ddof=1)
-    ess_g, _ = nuts.ess_mcse(per_chain_gpu)
-    ess_r, _ = nuts.ess_mcse(ref['per_chain'])
-    rel = np.abs(vg / vr - 1.0)
+    rel = np.abs(vg / ref['var'] - 1.0)
     # batch-means ESS is optimistic for variances (they mix slower than means): halve it
-    tolv = 4.0 * np.sqrt(2.0 / np.maximum(0.5 * ess_g, 10) + 2.0 / np.maximum(0.5 * ess_r, 10))
+    tolv = 4.0 * np.sqrt(2.0 / np.maximum(0.5 * ess_g, 10) + 2.0 / np.maximum(0.5 * ref['ess'], 10))
     assert np.all(rel < tolv), (rel / tolv).max()
 
 
@@ -104,7 +102,6 @@ def test_sampler_vs_oracle_nuts(model, J, n, D, C):
     site = synth.make_site(model, n, D, J, seed=21)
     NS = 6
     ctx = make_ctx(model, [site] * NS)           # identical sites: independent replicas
-    td = synth.oracle_density(model, site)
     iters, warm = 1000, 400
     seeds = [101 * (k + 1) for k in range(NS)]
     msteps, mrhat, nleap, secs = ctx.tilted_sample(seeds, C, iters, warm)
@@ -114,13 +111,11 @@ def test_sampler_vs_oracle_nuts(model, J, n, D, C):
     # the m3b/m4b tilted densities are funnels: an occasional chain lingers in the
     # neck (the fp64 oracle shows the same), so judge the replicas collectively
     assert np.median(mrhat) < 1.1, mrhat
-    ref = nuts.sample(lambda q: tuple(v[0] for v in td.lp_grad(q[None])), td.p, chains=8,
-                      n_iter=2500, n_warmup=500, seed=3)
-    ref_phi = dict(draws=ref['draws'][:, :td.d], per_chain=[c[:, :td.d] for c in ref['per_chain']])
+    # fp64 oracle NUTS, 8 chains x 2500 iterations on the same site (cached: tests/oracle_refs.py)
+    ref_phi = oracle_refs.summary(model, J, n, D)
     # step size and work per draw track the fp64 sampler
-    assert 0.6 < np.median(msteps) / ref['stepsize'] < 1.6
-    evals_ref = ref['n_grad'] / (8 * 2500.0)
-    assert 0.5 < np.median(nleap) / (C * iters) / evals_ref < 2.0
+    assert 0.6 < np.median(msteps) / ref_phi['stepsize'] < 1.6
+    assert 0.5 < np.median(nleap) / (C * iters) / ref_phi['evals_per_draw'] < 2.0
     failures = 0
     for k in range(NS):
         x = dr[k].T
@@ -171,18 +166,7 @@ def test_init_prev_and_zero_init():
     ctx.close()
 
 
-def _ep_problem(model, K, n_k, D, seed):
-    rng = np.random.RandomState(seed)
-    X = rng.standard_normal((K * n_k, D)) * 0.8
-    beta = rng.standard_normal(D) * 0.7
-    alpha = 0.6 * rng.standard_normal(K)
-    bk = np.repeat(beta[None], K, axis=0) + (0.0 if model == 'm1b' else 0.3 * rng.standard_normal((K, D)))
-    k_ind = np.repeat(np.arange(K), n_k)
-    f = alpha[k_ind] + np.einsum('nd,nd->n', X, bk[k_ind])
-    y = (rng.uniform(size=K * n_k) < 1 / (1 + np.exp(-f))).astype(np.int64)
-    d = dens.dphi(model, D)
-    prior = {'Q': np.eye(d) / 1.5 ** 2, 'r': np.zeros(d)}
-    return X, y, prior, d
+_ep_problem = oracle_refs.ep_problem
 
 
 @pytest.mark.parametrize('model', ['m1b', 'm4b'])
@@ -198,19 +182,11 @@ def test_full_ep_vs_oracle_ep(model):
     assert np.all(np.isfinite(ms)) and np.all(stimes > 0) and np.all(msteps > 0) and np.all(mrhats < 3.0)
     assert m.Qi.shape == (d, d, K) and np.allclose(m.Q, m.Q0 + m.Qi.sum(axis=2), rtol=1e-12, atol=1e-12)
 
-    st = orc.EPState(prior['Q'], prior['r'], K)
-    dens_k = [dens.TiltedDensity(model, X[k * n_k:(k + 1) * n_k], y[k * n_k:(k + 1) * n_k],
-                                 np.zeros(d), np.eye(d)) for k in range(K)]
-
-    def draw_fn(it, k, cav_m, cav_P):
-        td = dens_k[k]
-        td.mu, td.Omega = cav_m, cav_P
-        res = nuts.sample(lambda q: tuple(v[0] for v in td.lp_grad(q[None])), td.p, chains=C,
-                          n_iter=siter, seed=1000 * it + k)
-        return res['draws'][:, :d]
-
-    oinfo, oms, oSs = orc.run_ep(st, draw_fn, niter, lambda i: 0.6)
-    assert oinfo == 0
+    # oracle EP on the same problem: oracle NUTS (4 x 400 per site and iteration) + oracle moment
+    # matching / updates, 6 iterations, damping 0.6 (cached: tests/oracle_refs.py)
+    oref = oracle_refs.ep_reference(model)
+    assert int(oref['info']) == 0
+    oms, oSs = [oref['m']], [oref['S']]
     kl = orc.kl_mvn(oms[-1], oSs[-1], ms[-1], Ss[-1])
     # both runs carry Monte-Carlo noise from 4 x 200 draws per site per iteration
     assert kl < 0.25, kl

@@ -35,3 +35,24 @@ def test_adaptation_schedule():
     assert ends == [99, 149, 249, 449, 949]
     w = nuts.VarWindows(10, 1)
     assert all(w.learn(np.zeros(1)) is None for _ in range(10))
+
+
+def test_cached_oracle_references_are_current():
+    """tests/golden/nuts_ref.npz (oracle NUTS / oracle EP results used by the GPU sampler tests) holds
+    every case, and re-running the oracle reproduces the stored numbers (same seeds, same code)."""
+    import oracle_refs
+    cache = oracle_refs._load()
+    for case in oracle_refs.SAMPLER_CASES:
+        for k in ('mean', 'var', 'ess', 'mcse', 'stepsize', 'evals_per_draw'):
+            assert 'nuts_%s_%d_%d_%d_' % case + k in cache
+    for model in oracle_refs.EP_MODELS:
+        assert 'ep_%s_m' % model in cache and int(cache['ep_%s_info' % model]) == 0
+    case = oracle_refs.SAMPLER_CASES[0]
+    fresh = oracle_refs.compute_summary(*case)
+    stored = oracle_refs.summary(*case)
+    # same seeds: normally identical; a different BLAS build may change low-order bits and with them the
+    # trajectories, so the check is statistical
+    assert np.all(np.abs(fresh['mean'] - stored['mean']) < 4.0 * np.sqrt(2.0) * stored['mcse'])
+    assert np.all(np.abs(fresh['var'] / stored['var'] - 1.0) < 0.3)
+    assert abs(fresh['stepsize'] / stored['stepsize'] - 1.0) < 0.2
+    assert abs(fresh['evals_per_draw'] / stored['evals_per_draw'] - 1.0) < 0.3
