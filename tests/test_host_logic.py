@@ -93,3 +93,56 @@ def test_c_abi_surface():
     if not has_gpu:
         with pytest.raises(_lib.EpgError):
             _lib.Context(0)
+
+
+def test_site_partition_properties():
+    """Size-independent properties of the host-side partitions (hypothesis): `distribute_groups` keeps
+    every observation exactly once, in order, with within-site group indices 0..J_k-1; `Comm.shard`
+    tiles the sites over the ranks in contiguous, balanced blocks."""
+    from hypothesis import given, settings, strategies as st
+    from epstan.util import distribute_groups
+    from epstan._comm import Comm
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.lists(st.integers(1, 30), min_size=3, max_size=40), st.data())
+    def merge(Nj, data):
+        J = len(Nj)
+        K = data.draw(st.integers(2, J - 1))
+        Nk, Nj_k, j_ind_k = distribute_groups(J, K, np.array(Nj))
+        assert len(Nk) == K and Nk.sum() == sum(Nj) and Nj_k.sum() == J and np.all(Nj_k >= 1)
+        assert j_ind_k.shape == (sum(Nj),)
+        row, grp = 0, 0
+        for k in range(K):                              # groups stay whole, adjacent and ordered
+            assert Nk[k] == sum(Nj[grp:grp + Nj_k[k]])
+            seg = j_ind_k[row:row + Nk[k]]
+            assert np.array_equal(seg, np.repeat(np.arange(Nj_k[k]), Nj[grp:grp + Nj_k[k]]))
+            row += Nk[k]
+            grp += Nj_k[k]
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.lists(st.integers(1, 30), min_size=2, max_size=12), st.data())
+    def split(Nj, data):
+        J, N = len(Nj), sum(Nj)
+        if N <= J:
+            return
+        K = data.draw(st.integers(J + 1, N))
+        Nk, parts, none = distribute_groups(J, K, np.array(Nj))
+        assert none is None and len(Nk) == K and parts.sum() == K and np.all(Nk >= 1)
+        assert np.array_equal(np.add.reduceat(Nk, np.concatenate(([0], np.cumsum(parts)[:-1]))), Nj)
+
+    @settings(max_examples=100, deadline=None)
+    @given(st.integers(1, 5000), st.integers(1, 64))
+    def shards(K, size):
+        edges = []
+        for rank in range(size):
+            c = Comm()
+            c.rank, c.size = rank, size
+            edges.append(c.shard(K))
+        assert edges[0][0] == 0 and edges[-1][1] == K
+        assert all(edges[i][1] == edges[i + 1][0] for i in range(size - 1))
+        lens = [b - a for a, b in edges]
+        assert max(lens) - min(lens) <= 1 and lens == sorted(lens, reverse=True)
+
+    merge()
+    split()
+    shards()
