@@ -95,6 +95,45 @@ def test_c_abi_surface():
             _lib.Context(0)
 
 
+def test_c_abi_from_plain_c(tmp_path):
+    """The boundary is usable from C: the header compiles as C99 (no C++ or torch types) and a C
+    program that dlopens the library resolves every entry point and gets a loud failure, not a
+    fallback, from epg_create on a machine without a GPU."""
+    import shutil
+    import subprocess
+    if shutil.which('gcc') is None:
+        pytest.skip('no gcc')
+    from epstan import _lib
+    names = sorted(name for name, _, _ in _lib.SYMBOLS)
+    src = tmp_path / 'abi.c'
+    src.write_text(
+        '#include <dlfcn.h>\n#include <stdio.h>\n#include "epgpu.h"\n'
+        'static const char* names[] = {%s};\n'
+        'int main(int argc, char** argv) {\n'
+        '    void* h = dlopen(argv[1], RTLD_NOW | RTLD_LOCAL);\n'
+        '    if (!h) { fprintf(stderr, "%%s\\n", dlerror()); return 2; }\n'
+        '    for (unsigned i = 0; i < sizeof(names) / sizeof(names[0]); ++i)\n'
+        '        if (!dlsym(h, names[i])) { fprintf(stderr, "missing %%s\\n", names[i]); return 3; }\n'
+        '    int (*version)(void) = (int (*)(void))dlsym(h, "epg_version");\n'
+        '    int (*create)(epg_ctx**, int, void*, int) = (int (*)(epg_ctx**, int, void*, int))dlsym(h, "epg_create");\n'
+        '    epg_ctx* ctx = 0;\n'
+        '    int rc = create(&ctx, 0, 0, 1);\n'
+        '    printf("%%d %%d %%d\\n", version(), rc, ctx != 0);\n'
+        '    return 0;\n}\n' % ', '.join('"%s"' % n for n in names))
+    exe = tmp_path / 'abi'
+    subprocess.run(['gcc', '-std=gnu99', '-Wall', '-Werror', '-I', os.path.join(ROOT, 'include'), str(src),
+                    '-o', str(exe), '-ldl'], check=True)
+    out = subprocess.run([str(exe), _lib.LIB_PATH], check=True, capture_output=True, text=True).stdout.split()
+    assert out[0] == '1'
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    if not has_gpu:
+        assert int(out[1]) != 0 and out[2] == '0'
+
+
 def test_site_partition_properties():
     """Size-independent properties of the host-side partitions (hypothesis): `distribute_groups` keeps
     every observation exactly once, in order, with within-site group indices 0..J_k-1; `Comm.shard`
