@@ -185,3 +185,24 @@ def test_site_partition_properties():
     merge()
     split()
     shards()
+
+
+def test_bench_problem_is_shard_consistent():
+    """bench.py generates every site from its own seed, so a rank that builds only its shard holds the
+    same rows as the single-GPU run (the N-GPU bench lines measure the same problem)."""
+    if ROOT not in sys.path:
+        sys.path.insert(0, ROOT)
+    import bench
+    K, n_k, D = 6, 40, 5
+    Xf, yf, prior = bench.build_problem('m3b', K, n_k, D, 0, K)
+    for size in (2, 4):
+        for rank in range(size):
+            base, rem = divmod(K, size)
+            k0 = rank * base + min(rank, rem)
+            k1 = k0 + base + (1 if rank < rem else 0)
+            Xs, ys, _ = bench.build_problem('m3b', K, n_k, D, k0, k1)
+            assert np.array_equal(Xs[k0 * n_k:k1 * n_k], Xf[k0 * n_k:k1 * n_k])
+            assert np.array_equal(ys[k0 * n_k:k1 * n_k], yf[k0 * n_k:k1 * n_k])
+            assert not Xs[:k0 * n_k].any() and not Xs[k1 * n_k:].any()
+    assert prior['Q'].shape == (D + 1, D + 1) and set(np.unique(yf)) <= {0, 1}
+    assert abs(bench.default_df0(32)(1) - 0.5) < 1e-15
