@@ -394,7 +394,7 @@ def main():
                                   'unit': 'GB/s per GPU (L2 -> shared memory)', 'hbm_peak': hbm_peak}},
         'info': int(info), 'mean_stepsize': float(np.mean(msteps)), 'max_rhat': float(np.max(mrhats)),
     }
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:          # (the CPU baseline is reported at N=1 only)
         cores = os.cpu_count() or 1
         n_sample = min(K, max(cores, 2))
         cits, cgps, cwall = cpu_baseline(model, K, n_k, D, chains, siter, n_sample, cores)
