@@ -21,6 +21,7 @@ size_t epg_array_elems(const epg_ctx* c, int a) {
         case EPG_Q: case EPG_Q0: case EPG_S: return d * d;
         case EPG_R: case EPG_R0: case EPG_M: return d;
         case EPG_PARTIAL: return d * d + d + 1;
+        case EPG_DSUM: return d * d + d + 2;
         default: return 0;
     }
 }
@@ -94,6 +95,7 @@ void epg_destroy(epg_ctx* c) {
     if (c->draws) cudaFree(c->draws);
     if (c->scratch) cudaFree(c->scratch);
     if (c->util_buf) cudaFree(c->util_buf);
+    if (c->snr_buf) cudaFree(c->snr_buf);
     if (c->h_flags) cudaFreeHost(c->h_flags);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;

@@ -1209,6 +1209,17 @@ __device__ void site_analytics(const SamplerArgs& a, const SiteView& sv, const C
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) worst = fmaxf(worst, __shfl_xor_sync(0xffffffffu, worst, o));
+    // a chain that never found a finite starting point (PH_DEAD) has written no draws: poison its slice of
+    // the draw buffer so that moment matching fails the site (Stan raises on an initialisation failure;
+    // the reference then zero-fills the site update, method.py:460-465) instead of matching stale draws
+    for (int c = 0; c < C; ++c) {
+        if (cs[c].phase == PH_DONE) continue;
+        double* dst = a.draws + (size_t)sv.k * a.d * a.n_draws;
+        for (int e = lane; e < a.d * per; e += 32) {
+            const int i = e / per, t = e - i * per;
+            dst[(size_t)i * a.n_draws + c * per + t] = NAN;
+        }
+    }
     if (lane == 0) {
         double eps_mean = 0.0, nl = 0.0, nd = 0.0;
         int ok = 0;

@@ -32,6 +32,9 @@ class Comm(object):
     def barrier(self):
         pass
 
+    def sync_device(self):
+        pass
+
 
 class TorchComm(Comm):
     """torch.distributed process group (NCCL over NVLink on the GPU box, gloo in
@@ -82,6 +85,12 @@ class TorchComm(Comm):
 
     def barrier(self):
         self._dist.barrier(group=self.group)
+
+    def sync_device(self):
+        """Wait until the collectives issued so far (torch's current stream) have completed."""
+        import torch
+        if torch.cuda.is_available():
+            torch.cuda.current_stream().synchronize()
 
 
 def default_comm():

@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(os.path.dirname(_HERE), 'libepgpu.so')
 
 # enum epg_array
-(Q, R, Q0, R0, QI, RI, QI2, RI2, DQI, DRI, CAVQ, CAVM, S, M, PARTIAL, TMEAN) = range(16)
+(Q, R, Q0, R0, QI, RI, QI2, RI2, DQI, DRI, CAVQ, CAVM, S, M, PARTIAL, TMEAN, DSUM) = range(17)
 MODEL_IDS = {'m1b': 1, 'm2b': 2, 'm3b': 3, 'm4b': 4, 'm5b': 5}
 PREC_ESTIM = {'sample': 0, 'olse': 1}
 
@@ -56,6 +56,8 @@ SYMBOLS = [
     ('epg_accept', C.c_int, [C.c_void_p]),
     ('epg_global_moments', C.c_int, [C.c_void_p, _c_double_p, _c_double_p]),
     ('epg_force_pd', C.c_int, [C.c_void_p, C.c_double, C.c_double, _c_int32_p, _c_double_p]),
+    ('epg_delta_sums', C.c_int, [C.c_void_p]),
+    ('epg_delta_snr', C.c_int, [C.c_void_p, _c_double_p]),
     ('epg_damp_sweep', C.c_int, [C.c_void_p, C.c_int, _c_double_p, _c_double_p, _c_double_p,
                                  _c_double_p, _c_double_p]),
     ('epg_invert_normal_params', C.c_int, [C.c_void_p, C.c_int, C.c_int, _c_double_p, _c_double_p, C.c_int,
@@ -115,7 +117,16 @@ class Context:
                            "(libepgpu has no CPU fallback)".format(device))
         self._h = h
         self.device = int(device)
+        self.stream = None if own else int(stream)
         self.K = self.d = 0
+
+    def on_torch_stream(self):
+        """True when the context issues its work on torch's current stream of its device (so that
+        torch.distributed collectives are stream-ordered with the kernels)."""
+        if self.stream is None:
+            return False
+        import torch
+        return int(torch.cuda.current_stream(self.device).cuda_stream) == self.stream
 
     def close(self):
         if getattr(self, '_h', None):
@@ -163,6 +174,29 @@ class Context:
             'shape': (self.d * self.d + self.d + 1,), 'typestr': '<f8',
             'data': (int(self.device_ptr(PARTIAL)), False), 'version': 2}
         return torch.as_tensor(a, device=torch.device('cuda', self.device))
+
+    def _alias(self, array, n):
+        import torch
+
+        class _Alias(object):
+            pass
+        a = _Alias()
+        a.__cuda_array_interface__ = {'shape': (n,), 'typestr': '<f8',
+                                      'data': (int(self.device_ptr(array)), False), 'version': 2}
+        return torch.as_tensor(a, device=torch.device('cuda', self.device))
+
+    def dsum_tensor(self):
+        """torch view (no copy) of EPG_DSUM = [sum dQi | sum dri | sum |delta_k|^2 | n_ok]."""
+        return self._alias(DSUM, self.d * self.d + self.d + 2)
+
+    def delta_sums(self):
+        self._ck(self._lib.epg_delta_sums(self._h))
+
+    def delta_snr(self):
+        """(|sum_k delta_k|^2, sum_k |delta_k|^2, n_ok) of the (all-reduced) EPG_DSUM."""
+        out = np.empty(3)
+        self._ck(self._lib.epg_delta_snr(self._h, _dp(out)))
+        return float(out[0]), float(out[1]), int(round(out[2]))
 
     def sync(self):
         self._ck(self._lib.epg_sync(self._h))

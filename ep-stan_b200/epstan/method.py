@@ -149,6 +149,14 @@ class Worker(object):
         self.last_n_leapfrog = 0
         self.saved_samples = None
 
+        if self.builtin:
+            # the built-in sampler keeps every post-warm-up draw and starts from 'random', '0' or the
+            # previous draws: anything else would silently change the number of draws / the estimator
+            if self.stan_params['thin'] != 1:
+                raise ValueError("built-in sampler supports thin=1 only (got thin={})".format(
+                    self.stan_params['thin']))
+            if self.stan_params['init'] not in ('random', '0', 0):
+                raise ValueError("built-in sampler supports init 'random' or '0' only")
         self.init_prev = options['init_prev']
         self.init_orig = self.stan_params['init']
         if self.init_prev and not isinstance(self.init_orig, str):
@@ -340,7 +348,11 @@ class Master(object):
         df0               = None,
         df_decay          = 0.8,
         df_treshold       = 1e-6,
-        overwrite_model   = False
+        overwrite_model   = False,
+        # extensions (not in the reference): automatic damping selection, see `_select_df`
+        df_select         = None,
+        df_min            = None,
+        df_snr_z          = 2.0
     )
 
     # hooks (tests substitute a CPU double for the context / a communicator)
@@ -471,6 +483,16 @@ class Master(object):
         else:
             self.df0 = kwargs['df0']
 
+        self.df_select = kwargs['df_select']
+        if self.df_select not in (None, 'snr'):
+            raise ValueError("Arg. `df_select` has to be None or 'snr'")
+        if self.df_select == 'snr' and kwargs['df0'] is None:
+            self.df0 = lambda i: 1.0              # the selection rule picks below this cap
+        self.df_min = min(1.0 / self.K, 0.2) if kwargs['df_min'] is None else float(kwargs['df_min'])
+        self.df_snr_z = float(kwargs['df_snr_z'])
+        # per-iteration record of the last run(): damping used, update attempts, selection statistics
+        self.history = dict(df=[], attempts=[], snr=[], n_ok=[])
+
         # host mirrors (reference method.py:836-851), F-order as the reference
         self.S = np.empty((d, d), order='F')
         self.m = np.empty(d)
@@ -493,6 +515,7 @@ class Master(object):
         # when True, run() leaves the state on the GPU between calls: the host
         # mirrors are neither uploaded first nor refreshed afterwards (sync_host())
         self.keep_on_device = False
+        self._host_stale = False      # the device state is newer than the host mirrors (keep_on_device runs)
         self.n_leapfrog_total = 0     # gradient evaluations spent by the built-in sampler (local sites)
 
         # shard + device context
@@ -570,10 +593,49 @@ class Master(object):
                 arr[...] = self.comm.allgather_sites(loc, self.K, ax)
             else:
                 arr[...] = loc
+        self._host_stale = False
+
+    def _allreduce_device(self, tensor):
+        """Sum a device buffer of the context over the ranks.  The collective runs on torch's
+        current stream; when the context works on another stream the two are ordered explicitly."""
+        if self.comm.size <= 1:
+            return
+        ctx = self._shard.ctx
+        same = getattr(ctx, 'on_torch_stream', lambda: True)()
+        if not same:
+            ctx.sync()                       # kernels that wrote the buffer have finished
+        self.comm.allreduce_sum_(tensor)
+        if not same:
+            self.comm.sync_device()          # the reduced values are visible to the context's stream
 
     def _allreduce_partial(self):
         if self.comm.size > 1:
-            self.comm.allreduce_sum_(self._shard.ctx.partial_tensor())
+            self._allreduce_device(self._shard.ctx.partial_tensor())
+
+    def _select_df(self, cap):
+        """Automatic damping (`df_select='snr'`; extension).
+
+        At an EP fixed point every site delta has zero mean: the summed update is the sum of K
+        independent Monte Carlo errors.  With T2 = |sum_k delta_k|^2 and N2 = the K/(K-1)-corrected
+        sum_k |delta_k - mean|^2 in the Fisher metric of the current approximation, 1 - N2/T2 is
+        the positive-part shrinkage estimate of the fraction of the summed update that is signal
+        (the damping that minimises the expected squared distance to the fixed point).  The
+        estimate is taken `df_snr_z` standard errors low, capped by `df0(iter)` and floored at
+        `df_min` (default min(1/K, 0.2), the reference's asymptotic damping, fit.py:176-186)."""
+        ctx = self._shard.ctx
+        ctx.delta_sums()
+        self._allreduce_device(ctx.dsum_tensor())
+        T2, S2, n_ok = ctx.delta_snr()
+        d = self.dphi
+        dof = d * (d + 1) / 2.0 + d
+        raw = 0.0
+        N2 = float('nan')
+        if n_ok >= 2 and T2 > 0.0:
+            N2 = max(S2 - T2 / n_ok, 0.0) * n_ok / (n_ok - 1.0)
+            raw = 1.0 - (1.0 + self.df_snr_z * np.sqrt(2.0 / dof)) * N2 / T2
+        df = min(cap, max(self.df_min, raw))
+        self.history['snr'].append((T2, N2, raw))
+        return df
 
     def _all_ranks(self, flag):
         if self.comm.size > 1:
@@ -693,6 +755,8 @@ class Master(object):
         def result(info):
             if not self.keep_on_device:
                 self._pull_state()
+            else:
+                self._host_stale = True
             out = [info]
             if calc_moments:
                 out.append((m_phi_s, cov_phi_s))
@@ -701,7 +765,12 @@ class Master(object):
             return tuple(out) if len(out) > 1 else out[0]
 
         if not self.keep_on_device:
+            if self._host_stale:
+                # an earlier keep_on_device run left newer state on the device: refresh the mirrors
+                # first instead of overwriting the device with the stale host copies
+                self._pull_state()
             self._push_state(with_cavity=True)
+        self.history = dict(df=[], attempts=[], snr=[], n_ok=[])
         local_workers = self.workers[sh.k_begin:sh.k_end]
 
         for cur_iter in range(niter):
@@ -721,6 +790,8 @@ class Master(object):
                 return result(self.INFO_ALL_SITES_FAIL)
 
             def gmax(vals):
+                # (NaN = a site whose chains could not be initialised: it is a failed site, not a maximum)
+                vals = [v for v in vals if v is not None and np.isfinite(v)]
                 v = max(vals) if vals else -np.inf
                 return comm.allreduce_scalar(v, 'max') if comm.size > 1 else v
             stimes[cur_iter] = gmax([w.last_time for w in local_workers])
@@ -731,10 +802,15 @@ class Master(object):
 
             start_othertime = time.time()
             df = self.df0(self.iter)
+            if self.df_select == 'snr':
+                df = self._select_df(df)
+            df_first = df
             if verbose:
                 print("Iter {}, starting df {:.3g}".format(self.iter, df))
             failed_force_pos_def = False
+            attempts = 0
             while True:
+                attempts += 1
                 # Qi2 = Qi + df dQi, Q = Q0 + sum_k Qi2 (method.py:1071-1074); the
                 # all-reduce is the only exchange between GPUs
                 ctx.update_partial(df)
@@ -744,6 +820,9 @@ class Master(object):
                     ok = self._all_ranks(ctx.cavity(proposal=True)[1])
                     if ok:
                         ctx.accept()
+                        self.history['df'].append(df)
+                        self.history['attempts'].append(attempts)
+                        self.history['n_ok'].append(n_ok)
                         break
                     what = "cavity"
                 else:
@@ -759,7 +838,7 @@ class Master(object):
                 if df < self.df_treshold:
                     if verbose:
                         print("\nDamping factor reached minimum.")
-                    df = self.df0(self.iter)
+                    df = df_first
                     ctx.update_partial(df)          # Qi2 = Qi + df0 dQi  (method.py:1105-1107)
                     if failed_force_pos_def:
                         if verbose:

@@ -54,7 +54,9 @@ enum epg_array {
     EPG_PARTIAL = 14, /* [sum_k Qi2 | sum_k ri2 | n_ok] of this shard, d*d+d+1: the
                          NCCL all-reduce payload (method.py:1073-1074)     */
     EPG_TMEAN = 15, /* tilted means of the last moment matching  K*d (Worker.vec after tilted) */
-    EPG_NARRAYS = 16
+    EPG_DSUM = 16,  /* [sum_k dQi | sum_k dri | sum_k |delta_k|^2 | n_ok] of this shard, d*d+d+2
+                       (epg_delta_sums; all-reduced by the caller before epg_delta_snr)  */
+    EPG_NARRAYS = 17
 };
 
 /* ---- tilted log-density families (experiment/models/<name>[_sg].stan) ---- */
@@ -118,6 +120,18 @@ int epg_global_moments(epg_ctx* ctx, double* m_out, double* S_out);
  * lam = lambda_min(Qi2_k); if lam < thr: diag(Qi_k) += min_eig - lam.
  * forced_out[K], lam_out[K] may be NULL. */
 int epg_force_pd(epg_ctx* ctx, double thr, double min_eig, int32_t* forced_out, double* lam_out);
+
+/* ---- automatic damping selection (find_damp.py:144-183, fit.py:176-186) ----
+ * Signal-to-noise statistics of the site updates in the Fisher metric of the
+ * current global approximation N(m, S = Q^-1):
+ *     |(A, a)|^2 = 1/4 tr(S A S A) + 1/2 (a - A m)' S (a - A m)
+ * epg_delta_sums (call right after epg_moments): EPG_DSUM = [sum_k dQi | sum_k dri |
+ *   sum_k |delta_k|^2 | n_ok] over the local sites.  The caller all-reduces EPG_DSUM.
+ * epg_delta_snr: stats_out[3] = { |sum_k delta_k|^2, sum_k |delta_k|^2, n_ok } of the
+ *   (reduced) EPG_DSUM.  At an EP fixed point the first is the K-site sum of
+ *   independent zero-mean noise, i.e. about equal to the second. */
+int epg_delta_sums(epg_ctx* ctx);
+int epg_delta_snr(epg_ctx* ctx, double* stats_out);
 
 /* ---- damping sweep: experiment/find_damp.py:144-174 + kl_mvn :32-51 ----
  * For each dfs[i]: rebuild the global approximation from (Qi,ri,dQi,dri),

@@ -8,7 +8,7 @@ import torch
 
 from oracle import ep_linalg as orc
 
-(Q, R, Q0, R0, QI, RI, QI2, RI2, DQI, DRI, CAVQ, CAVM, S, M, PARTIAL, TMEAN) = range(16)
+(Q, R, Q0, R0, QI, RI, QI2, RI2, DQI, DRI, CAVQ, CAVM, S, M, PARTIAL, TMEAN, DSUM) = range(17)
 _SITE3 = (QI, QI2, DQI, CAVQ)
 _SITE2 = (RI, RI2, DRI, CAVM, TMEAN)
 
@@ -32,6 +32,9 @@ class OracleContext(object):
             self.a[i] = np.zeros(d)
         self.a[PARTIAL] = np.zeros(d * d + d + 1)
         self._partial_t = torch.from_numpy(self.a[PARTIAL])
+        self.a[DSUM] = np.zeros(d * d + d + 2)
+        self._dsum_t = torch.from_numpy(self.a[DSUM])
+        self._ok = np.ones(K, dtype=bool)
         self.draws = None
         self.U = None
 
@@ -58,6 +61,27 @@ class OracleContext(object):
 
     def partial_tensor(self):
         return self._partial_t
+
+    def dsum_tensor(self):
+        return self._dsum_t
+
+    def delta_sums(self):
+        d = self.d
+        S2 = sum(orc.fisher_norm2(self.a[Q], self.a[R], self.a[DQI][:, :, k], self.a[DRI][:, k])
+                 for k in range(self.K) if self._ok[k])
+        self.a[DSUM][:d * d] = self.a[DQI].sum(axis=2).ravel(order='F')
+        self.a[DSUM][d * d:d * d + d] = self.a[DRI].sum(axis=1)
+        self.a[DSUM][d * d + d] = S2
+        self.a[DSUM][d * d + d + 1] = self._ok.sum()
+
+    def delta_snr(self):
+        d = self.d
+        T2 = orc.fisher_norm2(self.a[Q], self.a[R], self.a[DSUM][:d * d].reshape(d, d, order='F'),
+                              self.a[DSUM][d * d:d * d + d])
+        return T2, float(self.a[DSUM][d * d + d]), int(round(self.a[DSUM][d * d + d + 1]))
+
+    def on_torch_stream(self):
+        return True
 
     def launch_count(self):
         return self._launches
@@ -90,6 +114,7 @@ class OracleContext(object):
             flags[k - k0] = ok
             self.a[DQI][:, :, k], self.a[DRI][:, k] = dQ, dr
             self.a[TMEAN][:, k] = self.draws[k].mean(axis=1)
+        self._ok[k0:k1] = flags
         return flags, int(flags.sum())
 
     def update_partial(self, df):

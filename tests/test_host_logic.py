@@ -206,3 +206,11 @@ def test_bench_problem_is_shard_consistent():
             assert not Xs[:k0 * n_k].any() and not Xs[k1 * n_k:].any()
     assert prior['Q'].shape == (D + 1, D + 1) and set(np.unique(yf)) <= {0, 1}
     assert abs(bench.default_df0(32)(1) - 0.5) < 1e-15
+    # the default bench data are the repository's simulators (== the reference's, golden) with seed 100:
+    # every rank simulates the same full data set
+    Xa, ya, pa = bench.build_problem('m3b', K, n_k, D, 0, 2, 'sim')
+    Xb, yb, pb = bench.build_problem('m3b', K, n_k, D, 4, 6, 'sim')
+    assert np.array_equal(Xa, Xb) and np.array_equal(ya, yb) and Xa.shape == (K * n_k, D)
+    assert np.allclose(np.diag(pa['Q']), 1 / 1.5 ** 2)
+    m0, S0 = np.zeros(3), np.eye(3)
+    assert abs(bench.kl_mvn(m0, S0, m0, S0)) < 1e-14 and bench.kl_mvn(m0, S0, m0 + 1, 2 * S0) > 0
