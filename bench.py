@@ -353,7 +353,7 @@ def run_ours(args, model, K, n_k, D, chains, siter):
             dist.barrier()
         torch.cuda.synchronize()
 
-    hist = dict(df=[], attempts=[], mrhat=[], mstep=[], stime=[], other=[], m=[], S=[])
+    hist = dict(df=[], attempts=[], mrhat=[], mstep=[], stime=[], other=[], m=[], S=[], rhat_sites=[], snr=[])
 
     def timed_run(nsteps, per_step_calls=False):
         """nsteps EP iterations: one run(nsteps) call, or nsteps calls of run(1) (the e2e leg: host state in and
@@ -372,6 +372,8 @@ def run_ours(args, model, K, n_k, D, chains, siter):
             done += n_done
             hist['df'] += list(m.history['df'])
             hist['attempts'] += list(m.history['attempts'])
+            hist['rhat_sites'] += list(m.history['rhat_sites'][:n_done])
+            hist['snr'] += list(m.history['snr'][:n_done])
             hist['mrhat'] += list(mrh_[:n_done])
             hist['mstep'] += list(mst_[:n_done])
             hist['stime'] += list(st_[:n_done])
@@ -487,6 +489,11 @@ def run_ours(args, model, K, n_k, D, chains, siter):
             'sampling_s': [round(float(v), 3) for v in hist['stime']],
             'kl_step': [round(v, 5) for v in kl_step],       # KL(iteration i || i-1) of the global approximation
             'all_rhat_below_1p1': bool(np.all(rh < 1.1)),
+            # per-site max split-Rhat over the site's sampled parameters (rank 0's shard): median, 90th
+            # percentile, share of sites above 1.1 -- `max_rhat` is the maximum of these over all sites
+            'rhat_sites_median_p90_frac_gt_1p1': [[round(float(x), 3) for x in t] for t in hist['rhat_sites']],
+            # damping selection: |sum_k delta_k|^2, noise estimate, raw signal fraction
+            'snr_T2_N2_raw': [[float('%.4g' % x) for x in t] for t in hist['snr']],
         },
     }
     if cpu_line is not None:

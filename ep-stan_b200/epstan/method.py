@@ -352,7 +352,7 @@ class Master(object):
         # extensions (not in the reference): automatic damping selection, see `_select_df`
         df_select         = None,
         df_min            = None,
-        df_snr_z          = 2.0
+        df_snr_z          = 3.0
     )
 
     # hooks (tests substitute a CPU double for the context / a communicator)
@@ -491,7 +491,7 @@ class Master(object):
         self.df_min = min(1.0 / self.K, 0.2) if kwargs['df_min'] is None else float(kwargs['df_min'])
         self.df_snr_z = float(kwargs['df_snr_z'])
         # per-iteration record of the last run(): damping used, update attempts, selection statistics
-        self.history = dict(df=[], attempts=[], snr=[], n_ok=[])
+        self.history = dict(df=[], attempts=[], snr=[], n_ok=[], rhat_sites=[])
 
         # host mirrors (reference method.py:836-851), F-order as the reference
         self.S = np.empty((d, d), order='F')
@@ -770,7 +770,7 @@ class Master(object):
                 # first instead of overwriting the device with the stale host copies
                 self._pull_state()
             self._push_state(with_cavity=True)
-        self.history = dict(df=[], attempts=[], snr=[], n_ok=[])
+        self.history = dict(df=[], attempts=[], snr=[], n_ok=[], rhat_sites=[])
         local_workers = self.workers[sh.k_begin:sh.k_end]
 
         for cur_iter in range(niter):
@@ -797,6 +797,12 @@ class Master(object):
             stimes[cur_iter] = gmax([w.last_time for w in local_workers])
             msteps[cur_iter] = gmax([w.last_msteps for w in local_workers])
             mrhats[cur_iter] = gmax([w.last_mrhat for w in local_workers])
+            # distribution of the per-site max split-Rhat behind that maximum (local shard)
+            rh = np.array([w.last_mrhat for w in local_workers if w.last_mrhat is not None], dtype=np.float64)
+            rh = rh[np.isfinite(rh)]
+            self.history['rhat_sites'].append(
+                (float(np.median(rh)), float(np.percentile(rh, 90)), float(np.mean(rh > 1.1))) if rh.size
+                else (float('nan'),) * 3)
             if verbose:
                 print("Sampling done, max sampling time {}".format(stimes[cur_iter]))
 

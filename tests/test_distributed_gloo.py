@@ -50,6 +50,54 @@ def _worker(rank, world, port, tag, ret):
         dist.destroy_process_group()
 
 
+def _worker_snr(rank, world, port, ret):
+    for p in (ROOT, os.path.join(ROOT, 'ep-stan_b200'), TESTS):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        import epstan.method as method
+        import fake_backend
+        import test_damping as td
+        from oracle import ep_linalg as orc
+        method.Master._context_factory = staticmethod(lambda dev, stream: fake_backend.OracleContext(dev, stream))
+        sc = td._scenario(K=9, d=5, chains=4, it=60, niter=5, seed=17, df0=orc.default_df0(9))
+        m = td._master(method, sc, df_select='snr')
+        info, (ms, Ss) = m.run(sc['niter'], verbose=False, seed=sc['seed'])
+        ret[rank] = dict(info=info, m=ms, S=Ss, df=list(m.history['df']), n_local=m._shard.n_local)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_and_three_rank_damping_selection():
+    """df_select='snr' over 2 and 3 ranks (uneven shards): the all-reduced statistics give every rank the
+    same damping as the single-process oracle replay."""
+    from conftest import relerr
+    sys.path.insert(0, TESTS)
+    import test_damping as td
+    from oracle import ep_linalg as orc
+    sc = td._scenario(K=9, d=5, chains=4, it=60, niter=5, seed=17, df0=orc.default_df0(9))
+    oinfo, oms, oSs, _, _ = td._oracle_run(sc, df_select='snr')
+    for world in (2, 3):
+        port = 29700 + (os.getpid() % 2000) + world
+        ctx = mp.get_context('spawn')
+        ret = ctx.Manager().dict()
+        procs = [ctx.Process(target=_worker_snr, args=(r, world, port, ret)) for r in range(world)]
+        for p in procs:
+            p.start()
+        for p in procs:
+            p.join(180)
+            assert p.exitcode == 0
+        assert sorted(ret.keys()) == list(range(world))
+        assert sum(ret[r]['n_local'] for r in range(world)) == 9
+        for r in range(world):
+            assert ret[r]['info'] == oinfo == 0
+            assert relerr(ret[r]['m'], oms) < 1e-10 and relerr(ret[r]['S'], oSs) < 1e-10
+            assert ret[r]['df'] == ret[0]['df']
+
+
 @pytest.mark.parametrize('tag', ['runA', 'runC', 'runD', 'runF'])
 def test_two_rank_master_matches_reference(golden, tag):
     from conftest import relerr
