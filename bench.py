@@ -340,6 +340,8 @@ def run_ours(args, model, K, n_k, D, chains, siter):
         kw['df_select'] = 'snr'
         if args.damp == 'auto1':
             kw['df0'] = None                   # no cap: the selection may take a full step
+    if args.rhat_max > 0:
+        kw['rhat_max'] = args.rhat_max
     m = method.Master('experiment/models/%s_sg' % model, X, y, site_sizes=np.full(K, n_k), prior=prior,
                       chains=chains, iter=siter, **kw)
     n_sample = min(K, max(os.cpu_count() or 1, 2))
@@ -353,7 +355,7 @@ def run_ours(args, model, K, n_k, D, chains, siter):
             dist.barrier()
         torch.cuda.synchronize()
 
-    hist = dict(df=[], attempts=[], mrhat=[], mstep=[], stime=[], other=[], m=[], S=[], rhat_sites=[], snr=[])
+    hist = dict(df=[], attempts=[], mrhat=[], mstep=[], stime=[], other=[], m=[], S=[], rhat_sites=[], snr=[], n_fail=[])
 
     def timed_run(nsteps, per_step_calls=False):
         """nsteps EP iterations: one run(nsteps) call, or nsteps calls of run(1) (the e2e leg: host state in and
@@ -374,6 +376,7 @@ def run_ours(args, model, K, n_k, D, chains, siter):
             hist['attempts'] += list(m.history['attempts'])
             hist['rhat_sites'] += list(m.history['rhat_sites'][:n_done])
             hist['snr'] += list(m.history['snr'][:n_done])
+            hist['n_fail'] += list(m.history['n_fail'][:n_done])
             hist['mrhat'] += list(mrh_[:n_done])
             hist['mstep'] += list(mst_[:n_done])
             hist['stime'] += list(st_[:n_done])
@@ -460,6 +463,7 @@ def run_ours(args, model, K, n_k, D, chains, siter):
                    'damping': {'auto': 'fit.py default_df0 as cap + automatic selection (df_select=snr)',
                                'auto1': 'automatic selection (df_select=snr), no cap',
                                'schedule': 'fit.py default_df0'}[args.damp],
+                   'rhat_max': args.rhat_max if args.rhat_max > 0 else None,
                    'l2': ('inputs larger than L2 (X %.0f MB fp32 + bf16 per GPU)' if x_bytes > 126e6
                           else 'inputs smaller than L2 (X %.0f MB fp32 + bf16 per GPU); not flushed: a step re-reads '
                                'each site\'s X thousands of times by design, the first touch is <0.1 %% of a step')
@@ -484,6 +488,7 @@ def run_ours(args, model, K, n_k, D, chains, siter):
             'ep_iterations_total': len(hist['df']),
             'df_used': [round(float(v), 6) for v in hist['df']],
             'update_attempts': [int(v) for v in hist['attempts']],
+            'sites_skipped': [int(v) for v in hist['n_fail']],     # failed moment estimate or Rhat > rhat_max
             'max_rhat': [round(float(v), 4) for v in hist['mrhat']],
             'mean_stepsize': [round(float(v), 5) for v in hist['mstep']],
             'sampling_s': [round(float(v), 3) for v in hist['stime']],
@@ -513,6 +518,8 @@ def main():
     ap.add_argument('--siter', type=int, default=None)
     ap.add_argument('--damp', default='auto', choices=['auto', 'auto1', 'schedule'])
     ap.add_argument('--data', default=None, choices=['sim', 'synth'])
+    ap.add_argument('--rhat-max', type=float, default=2.0,
+                    help='skip the update of sites whose max split-Rhat exceeds this (0: never, the reference)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
     model, K, n_k, D, chains, siter = WORKLOADS[args.workload]

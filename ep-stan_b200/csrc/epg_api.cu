@@ -234,6 +234,19 @@ int epg_moments(epg_ctx* c, int k0, int k1, int n, int prec_estim, int32_t* ok_o
     return 0;
 }
 
+int epg_fail_sites(epg_ctx* c, int n, const int32_t* sites) {
+    if (!c->arr[EPG_Q] || n < 0 || (n > 0 && !sites)) return epg_fail_msg(c, "epg_fail_sites: bad args/state");
+    const size_t d = c->d;
+    for (int i = 0; i < n; ++i) {
+        const int k = sites[i];
+        if (k < 0 || k >= c->K) return epg_fail_msg(c, "epg_fail_sites: bad site index");
+        EPG_CHECK(c, cudaMemsetAsync(c->arr[EPG_DQI] + d * d * k, 0, sizeof(double) * d * d, c->stream));
+        EPG_CHECK(c, cudaMemsetAsync(c->arr[EPG_DRI] + d * k, 0, sizeof(double) * d, c->stream));
+        EPG_CHECK(c, cudaMemsetAsync(c->site_ok + k, 0, sizeof(int), c->stream));
+    }
+    return 0;
+}
+
 int epg_update_partial(epg_ctx* c, double df) {
     if (!c->arr[EPG_Q]) return epg_fail_msg(c, "state not initialised");
     EPG_CHECK(c, epg_launch_update_partial(c, df));

@@ -32,6 +32,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <algorithm>
 #include <vector>
 
 #define NTHR 256
@@ -48,6 +49,9 @@ struct epg_site_data {
     int64_t N = 0;
     float* X = nullptr;                 // [N][S]
     __nv_bfloat16* Xb = nullptr;        // [N][64] bf16 copy for the tensor-core pass (column D = 1)
+    float* xmean = nullptr;             // [K][64] per-site column means the bf16 copy is centred on (0 beyond column D-1)
+    int* order = nullptr;               // [K] launch order of the sites: most expensive (gradient evaluations of the
+    std::vector<double> h_cost;         //     previous run, h_cost) first, so that stragglers do not start last
     CUtensorMap tmap;                   // TMA descriptor of Xb: box 64 x 128 rows, 128-byte swizzle
     bool tc_ok = false;                 // tensor-core pass usable (single group, D+1 <= 64)
     int use_tc = 1;                     // option (epg_set_option "use_tc")
@@ -77,6 +81,7 @@ struct epg_site_data {
 void epg_sites_free(epg_ctx* c) {
     epg_site_data* s = c->sites;
     if (!s) return;
+    cudaFree(s->xmean); cudaFree(s->order);
     cudaFree(s->X); cudaFree(s->Xb); cudaFree(s->y); cudaFree(s->row0); cudaFree(s->grp_ptr); cudaFree(s->grp_rows);
     cudaFree(s->chain_mem); cudaFree(s->last_q); cudaFree(s->omega); cudaFree(s->out); cudaFree(s->ld_buf);
     delete s;
@@ -101,12 +106,24 @@ __global__ void k_convert_x(const double* __restrict__ src, float* __restrict__ 
     const int c = (int)(idx - r * S);
     dst[idx] = c < D ? (float)src[r * D + c] : (c == D ? 1.0f : 0.0f);
 }
-__global__ void k_convert_xb(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t rows, int S) {
+// bf16 copy for the tensor-core pass, CENTRED per site: dst = bf16(x - mean_k[col]) for the D input columns
+// (column D stays 1, the rest 0).  bf16 keeps 8 significant bits: a column like 35.5 +- 0.02 (the simulators
+// shift the inputs of groups with extreme intercepts, common.py:132-317) would otherwise lose all of its
+// within-site variation.  The means re-enter exactly: f = (alpha + c'beta) + (x - c)'beta and
+// G_col = sum_n e_n (x - c)_col + c_col sum_n e_n  (coefficient build / chain rule of likelihood_pass_tc).
+__global__ void k_convert_xb(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t rows, int S, int D,
+                             const float* __restrict__ xmean, const int64_t* __restrict__ row0, int K) {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= rows * 64) return;
     const int64_t r = idx >> 6;
     const int c = (int)(idx & 63);
-    dst[idx] = __float2bfloat16(c < S ? src[r * S + c] : 0.0f);
+    float v = c < S ? src[r * S + c] : 0.0f;
+    if (c < D) {
+        int lo = 0, hi = K;                       // site of row r: row0[lo] <= r < row0[lo + 1]
+        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (row0[mid] <= r) lo = mid; else hi = mid; }
+        v -= xmean[(size_t)lo * 64 + c];
+    }
+    dst[idx] = __float2bfloat16(v);
 }
 __global__ void k_convert_y(const int64_t* __restrict__ src, float* __restrict__ dst, int64_t n) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -191,6 +208,8 @@ struct ChainStack { double lsw[MAXDEPTH_CAP], V[MAXDEPTH_CAP]; };
 struct SamplerArgs {
     // site data
     const float* X; const float* y; const int64_t* row0; const int* grp_ptr; const int* grp_rows;
+    const float* xmean;                // [K][64] column means of the centred bf16 copy (tensor-core pass)
+    const int* order;                  // launch order: block b samples site k0 + order[b] (nullptr: identity)
     int model, D, S, d;
     // cavity
     const double* cavQ; const double* cavm; float* omega;
@@ -539,23 +558,39 @@ __device__ void likelihood_pass_tc(const SamplerArgs& a, unsigned char* smem, un
     const int ia = four ? 1 : 0;
     const int ib = four ? 2 + D : 1;
     PROF_T(q0);
+    const float* xm = a.xmean + (size_t)k_local * tc::KW;            // column means of the centred design matrix
     if (worker) {
-        // coefficient operands B = B_hi + B_lo (bf16 each), K-major interleaved layout
-        for (int e = tid; e < nchains * tc::KW; e += NTHR) {       // (rows of unused chains stay zero from setup)
-            const int c = e / tc::KW, col = e - c * tc::KW;
-            float v = 0.0f;
-            if (col <= D) {
-                const float* q = cvec(a, SiteView{smem, k_local}, c, V_Q);
-                if (col == D) v = q[d] * __expf(q[ia]) + (four ? q[0] : 0.0f);
-                else if (model == EPG_M1B) v = q[1 + col];
-                else if (model == EPG_M2B) v = q[d + 1 + col] * __expf(q[ib]);
-                else v = q[d + 1 + col] * __expf(q[ib + col]) + (four ? q[2 + col] : 0.0f);
+        // coefficient operands B = B_hi + B_lo (bf16 each), K-major interleaved layout; one warp per chain,
+        // lane l builds columns l and l + 32.  The design matrix is centred, so the intercept coefficient
+        // (column D, which multiplies 1) carries the mean term:  alpha + sum_col mean_col * beta_col.
+        const int lane = tid & 31;
+        for (int c = tid >> 5; c < nchains; c += NWARP) {          // (rows of unused chains stay zero from setup)
+            const float* q = cvec(a, SiteView{smem, k_local}, c, V_Q);
+            float v[2];
+            float mterm = 0.0f;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int col = lane + 32 * h;
+                float b = 0.0f;
+                if (col < D) {
+                    if (model == EPG_M1B) b = q[1 + col];
+                    else if (model == EPG_M2B) b = q[d + 1 + col] * __expf(q[ib]);
+                    else b = q[d + 1 + col] * __expf(q[ib + col]) + (four ? q[2 + col] : 0.0f);
+                    mterm = fmaf(xm[col], b, mterm);
+                }
+                v[h] = b;
             }
-            const __nv_bfloat16 hi = __float2bfloat16(v);
-            const __nv_bfloat16 lo = __float2bfloat16(v - __bfloat162float(hi));
-            const int cc = tc::chain_col(c);
-            *reinterpret_cast<__nv_bfloat16*>(tcb + tc::Smem::BM + tc::interleave_off32(cc, col)) = hi;
-            *reinterpret_cast<__nv_bfloat16*>(tcb + tc::Smem::BM + tc::interleave_off32(tc::NCH + cc, col)) = lo;
+            mterm = warp_sum(mterm);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int col = lane + 32 * h;
+                if (col == D) v[h] = q[d] * __expf(q[ia]) + (four ? q[0] : 0.0f) + mterm;
+                const __nv_bfloat16 hi = __float2bfloat16(v[h]);
+                const __nv_bfloat16 lo = __float2bfloat16(v[h] - __bfloat162float(hi));
+                const int cc = tc::chain_col(c);
+                *reinterpret_cast<__nv_bfloat16*>(tcb + tc::Smem::BM + tc::interleave_off32(cc, col)) = hi;
+                *reinterpret_cast<__nv_bfloat16*>(tcb + tc::Smem::BM + tc::interleave_off32(tc::NCH + cc, col)) = lo;
+            }
         }
         tc::fence_proxy_async();
     }
@@ -577,7 +612,9 @@ __device__ void likelihood_pass_tc(const SamplerArgs& a, unsigned char* smem, un
         for (int e = tid; e < nchains * tc::KW; e += NTHR) {
             const int c = e / tc::KW, col = e - c * tc::KW;
             if (col > D) continue;
-            const float gsum = gout[tc::chain_col(c) * tc::KW + col] + gout[(tc::NCH + tc::chain_col(c)) * tc::KW + col];
+            float gsum = gout[tc::chain_col(c) * tc::KW + col] + gout[(tc::NCH + tc::chain_col(c)) * tc::KW + col];
+            if (col < D)                                   // centred inputs: + mean_col * sum_n e_n
+                gsum = fmaf(xm[col], gout[tc::chain_col(c) * tc::KW + D] + gout[(tc::NCH + tc::chain_col(c)) * tc::KW + D], gsum);
             const float* q = cvec(a, SiteView{smem, k_local}, c, V_Q);
             float* gl = cvec(a, SiteView{smem, k_local}, c, V_GL);
             if (col == D) {
@@ -606,9 +643,10 @@ __device__ void likelihood_pass_tc(const SamplerArgs& a, unsigned char* smem, un
                 const float* gout = reinterpret_cast<const float*>(tcb + tc::Smem::GOUT);
                 const float* q = cvec(a, SiteView{smem, k_local}, tid, V_Q);
                 float acc = 0.0f;
+                const float se = gout[tc::chain_col(tid) * tc::KW + D] + gout[(tc::NCH + tc::chain_col(tid)) * tc::KW + D];
                 for (int col = 0; col < D; ++col)
-                    acc = fmaf(q[d + 1 + col], gout[tc::chain_col(tid) * tc::KW + col] +
-                                                   gout[(tc::NCH + tc::chain_col(tid)) * tc::KW + col], acc);
+                    acc = fmaf(q[d + 1 + col], fmaf(xm[col], se, gout[tc::chain_col(tid) * tc::KW + col] +
+                                                                 gout[(tc::NCH + tc::chain_col(tid)) * tc::KW + col]), acc);
                 cvec(a, SiteView{smem, k_local}, tid, V_GL)[ib] = __expf(q[ib]) * acc;
             }
         }
@@ -1246,7 +1284,8 @@ __global__ void __launch_bounds__(USE_TC ? tc::NTHREADS : NTHR, 1)
 k_nuts(const SamplerArgs a, const __grid_constant__ CUtensorMap tmap) {
     extern __shared__ __align__(1024) unsigned char smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int k_local = a.k0 + blockIdx.x;
+    const int site_off = a.order ? a.order[blockIdx.x] : (int)blockIdx.x;    // most expensive sites first
+    const int k_local = a.k0 + site_off;
     const int C = a.C, d = a.d, D = a.D, S = a.S;
     const int64_t row_begin = a.row0[k_local];
     const int n_rows = (int)(a.row0[k_local + 1] - row_begin);
@@ -1285,7 +1324,7 @@ k_nuts(const SamplerArgs a, const __grid_constant__ CUtensorMap tmap) {
     __threadfence_block();
     __syncthreads();
 
-    const uint32_t site_seed = a.seeds[blockIdx.x];
+    const uint32_t site_seed = a.seeds[site_off];
     long long clk_chain = 0, clk_lik = 0, n_ticks = 0;
     for (;;) {
         const long long tk0 = clock64();
@@ -1366,8 +1405,9 @@ k_nuts_pp(const SamplerArgs a, const __grid_constant__ CUtensorMap tmap, int n_s
                     chain_group_sync();                 // everyone has read the flag before thread 0 may set it
                     if (ex) break;
                     if (ct == 0) {
-                        const int i = atomicAdd(queue, 1);
-                        if (i < n_sites) {
+                        const int qi = atomicAdd(queue, 1);
+                        if (qi < n_sites) {
+                            const int i = a.order ? a.order[qi] : qi;
                             const int k = a.k0 + i;
                             S.k = k; S.n_active = C; S.seed = a.seeds[i];
                             S.row_begin = a.row0[k];
@@ -1690,8 +1730,24 @@ int epg_upload_sites(epg_ctx* c, int model, int D, const int64_t* k_lim, const d
     memset(&s->tmap, 0, sizeof(s->tmap));
     if (s->Jmax == 1 && D + 1 <= tc::KW) {
         EPG_CHECK(c, cudaMalloc((void**)&s->Xb, sizeof(__nv_bfloat16) * (size_t)N * tc::KW));
+        // per-site column means (fp64 on the host, stored as fp32) the bf16 copy is centred on
+        std::vector<float> xm((size_t)K * tc::KW, 0.0f);
+        {
+            std::vector<double> acc(D);
+            for (int k = 0; k < K; ++k) {
+                std::fill(acc.begin(), acc.end(), 0.0);
+                const int64_t lo = s->h_row0[k], hi = s->h_row0[k + 1];
+                for (int64_t r = lo; r < hi; ++r) {
+                    const double* xr = X + (size_t)(base + r) * D;
+                    for (int j = 0; j < D; ++j) acc[j] += xr[j];
+                }
+                for (int j = 0; j < D; ++j) xm[(size_t)k * tc::KW + j] = (float)(acc[j] / (double)(hi - lo));
+            }
+        }
+        EPG_CHECK(c, cudaMalloc((void**)&s->xmean, sizeof(float) * xm.size()));
+        EPG_CHECK(c, cudaMemcpyAsync(s->xmean, xm.data(), sizeof(float) * xm.size(), cudaMemcpyHostToDevice, c->stream));
         const int64_t tot = N * tc::KW;
-        k_convert_xb<<<(unsigned)((tot + 255) / 256), 256, 0, c->stream>>>(s->X, s->Xb, N, S);
+        k_convert_xb<<<(unsigned)((tot + 255) / 256), 256, 0, c->stream>>>(s->X, s->Xb, N, S, D, s->xmean, s->row0, K);
         c->launches++;
         EPG_CHECK(c, cudaStreamSynchronize(c->stream));
         typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -1737,6 +1793,7 @@ int epg_num_params(epg_ctx* c, int k) {
 static int fill_args(epg_ctx* c, SamplerArgs& a, int C, int CP, int n_sites = 1, bool need_allhot = false) {
     epg_site_data* s = c->sites;
     a.X = s->X; a.y = s->y; a.row0 = s->row0; a.grp_ptr = s->grp_ptr; a.grp_rows = s->grp_rows;
+    a.xmean = s->xmean; a.order = nullptr;
     a.model = s->model; a.D = s->D; a.S = s->S; a.d = c->d;
     a.cavQ = c->arr[EPG_CAVQ]; a.cavm = c->arr[EPG_CAVM];
     a.P = s->Pmax; a.C = C;
@@ -1826,6 +1883,18 @@ int epg_tilted_sample(epg_ctx* c, int k0, int k1, const uint32_t* seeds, const e
     EPG_CHECK(c, cudaMemcpyAsync(dseeds, seeds, sizeof(uint32_t) * (k1 - k0), cudaMemcpyHostToDevice, c->stream));
     a.seeds = dseeds;
     a.draws = c->draws; a.n_draws = n; a.k0 = k0;
+    // launch order: sites that spent the most gradient evaluations in the previous run first (longest
+    // processing time first): a straggler -- e.g. an ill-conditioned site that saturates the tree depth on
+    // every transition -- must not start in the last wave
+    if ((int)s->h_cost.size() == c->K && k1 - k0 > 1) {
+        std::vector<int> ord(k1 - k0);
+        for (int i = 0; i < k1 - k0; ++i) ord[i] = i;
+        std::stable_sort(ord.begin(), ord.end(), [&](int x, int y) { return s->h_cost[k0 + x] > s->h_cost[k0 + y]; });
+        if (!s->order) EPG_CHECK(c, cudaMalloc((void**)&s->order, sizeof(int) * (size_t)c->K));
+        EPG_CHECK(c, cudaMemcpyAsync(s->order, ord.data(), sizeof(int) * ord.size(), cudaMemcpyHostToDevice, c->stream));
+        EPG_CHECK(c, cudaStreamSynchronize(c->stream));           // (ord is a local)
+        a.order = s->order;
+    }
 #ifdef EPG_TC_EXPERIMENT
     { int kn = getenv("EPGPU_KNOBS") ? atoi(getenv("EPGPU_KNOBS")) : 0; cudaMemcpyToSymbol(tc::g_knobs, &kn, sizeof(int)); }
 #endif
@@ -1861,7 +1930,9 @@ int epg_tilted_sample(epg_ctx* c, int k0, int k1, const uint32_t* seeds, const e
     EPG_CHECK(c, cudaMemcpyAsync(out.data(), s->out + (size_t)k0 * 8, sizeof(double) * out.size(),
                                  cudaMemcpyDeviceToHost, c->stream));
     EPG_CHECK(c, cudaStreamSynchronize(c->stream));
+    if ((int)s->h_cost.size() != c->K) s->h_cost.assign((size_t)c->K, 0.0);
     for (int i = 0; i < k1 - k0; ++i) {
+        s->h_cost[k0 + i] = out[8 * i + 6];                      // ticks = the site's sequential length
         if (msteps_out) msteps_out[i] = out[8 * i + 0];
         if (mrhat_out) mrhat_out[i] = out[8 * i + 1];
         if (n_leapfrog_out) n_leapfrog_out[i] = (int64_t)out[8 * i + 2];

@@ -51,6 +51,7 @@ SYMBOLS = [
     ('epg_set_draws', C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, _c_double_p]),
     ('epg_get_draws', C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, _c_double_p]),
     ('epg_moments', C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, _c_int32_p, C.POINTER(C.c_int)]),
+    ('epg_fail_sites', C.c_int, [C.c_void_p, C.c_int, _c_int32_p]),
     ('epg_update_partial', C.c_int, [C.c_void_p, C.c_double]),
     ('epg_update_finish', C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
     ('epg_accept', C.c_int, [C.c_void_p]),
@@ -234,6 +235,10 @@ class Context:
         self._ck(self._lib.epg_moments(self._h, k0, k1, n, mode,
                                        flags.ctypes.data_as(_c_int32_p), C.byref(n_ok)))
         return flags.astype(bool), n_ok.value
+
+    def fail_sites(self, sites):
+        sites = np.ascontiguousarray(sites, dtype=np.int32)
+        self._ck(self._lib.epg_fail_sites(self._h, len(sites), sites.ctypes.data_as(_c_int32_p)))
 
     def update_partial(self, df):
         self._ck(self._lib.epg_update_partial(self._h, float(df)))

@@ -352,7 +352,10 @@ class Master(object):
         # extensions (not in the reference): automatic damping selection, see `_select_df`
         df_select         = None,
         df_min            = None,
-        df_snr_z          = 3.0
+        df_snr_z          = 3.0,
+        # extension: a site whose max split-Rhat exceeds this is treated as failed for the iteration
+        # (its update is skipped like a failed moment estimate, method.py:460-465); None = never
+        rhat_max          = None
     )
 
     # hooks (tests substitute a CPU double for the context / a communicator)
@@ -490,8 +493,9 @@ class Master(object):
             self.df0 = lambda i: 1.0              # the selection rule picks below this cap
         self.df_min = min(1.0 / self.K, 0.2) if kwargs['df_min'] is None else float(kwargs['df_min'])
         self.df_snr_z = float(kwargs['df_snr_z'])
+        self.rhat_max = kwargs['rhat_max']
         # per-iteration record of the last run(): damping used, update attempts, selection statistics
-        self.history = dict(df=[], attempts=[], snr=[], n_ok=[], rhat_sites=[])
+        self.history = dict(df=[], attempts=[], snr=[], n_ok=[], rhat_sites=[], n_fail=[])
 
         # host mirrors (reference method.py:836-851), F-order as the reference
         self.S = np.empty((d, d), order='F')
@@ -708,6 +712,13 @@ class Master(object):
                 j += 1
             oks[i:j], _ = ctx.moments(n, mode, i, j)
             i = j
+        if self.rhat_max is not None and workers:
+            # chains that did not mix give unreliable moments: skip the site's update this round
+            bad = [i for i, w in enumerate(workers)
+                   if oks[i] and not (w.last_mrhat is not None and w.last_mrhat <= self.rhat_max)]
+            if bad:
+                ctx.fail_sites(bad)
+                oks[bad] = False
         for w, ok in zip(workers, oks):
             w.nsamp = n
             if w._mode_now() == 'sample' and w.prec_estim_skip > 0:
@@ -770,7 +781,7 @@ class Master(object):
                 # first instead of overwriting the device with the stale host copies
                 self._pull_state()
             self._push_state(with_cavity=True)
-        self.history = dict(df=[], attempts=[], snr=[], n_ok=[], rhat_sites=[])
+        self.history = dict(df=[], attempts=[], snr=[], n_ok=[], rhat_sites=[], n_fail=[])
         local_workers = self.workers[sh.k_begin:sh.k_end]
 
         for cur_iter in range(niter):
@@ -829,6 +840,7 @@ class Master(object):
                         self.history['df'].append(df)
                         self.history['attempts'].append(attempts)
                         self.history['n_ok'].append(n_ok)
+                        self.history['n_fail'].append(n_fail)
                         break
                     what = "cavity"
                 else:

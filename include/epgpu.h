@@ -104,6 +104,11 @@ int epg_set_draws(epg_ctx* ctx, int k0, int k1, int n, const double* draws);
 int epg_get_draws(epg_ctx* ctx, int k0, int k1, int n, double* draws);
 int epg_moments(epg_ctx* ctx, int k0, int k1, int n, int prec_estim, int32_t* ok_out, int* n_ok);
 
+/* Mark local sites as failed for this EP iteration: zero-fills their (dQi, dri) and clears their
+ * flags exactly as a failed moment estimate does (method.py:460-465).  Used by the host when a
+ * site's chains did not mix (Master option `rhat_max`, an extension). */
+int epg_fail_sites(epg_ctx* ctx, int n, const int32_t* sites);
+
 /* ---- damped update + aggregation: method.py:1071-1081 ----
  * epg_update_partial: Qi2 = Qi + df*dQi, ri2 = ri + df*dri for the local sites
  *   and EPG_PARTIAL = [sum Qi2 | sum ri2 | (unchanged)]            (a11)

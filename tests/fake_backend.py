@@ -117,6 +117,12 @@ class OracleContext(object):
         self._ok[k0:k1] = flags
         return flags, int(flags.sum())
 
+    def fail_sites(self, sites):
+        for k in sites:
+            self.a[DQI][:, :, k] = 0.0
+            self.a[DRI][:, k] = 0.0
+            self._ok[k] = False
+
     def update_partial(self, df):
         self.a[QI2][...] = self.a[QI] + df * self.a[DQI]
         self.a[RI2][...] = self.a[RI] + df * self.a[DRI]

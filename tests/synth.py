@@ -33,3 +33,13 @@ def bf16_round(x):
     u = np.asarray(x, dtype=np.float32).view(np.uint32).astype(np.uint64)
     u = ((u + 0x7FFF + ((u >> 16) & 1)) >> 16) << 16
     return u.astype(np.uint32).view(np.float32).astype(np.float64)
+
+
+def tc_stored_X(X):
+    """The design matrix as the tensor-core pass holds it (csrc/epg_sampler.cu k_convert_xb): centred on the
+    site's column means (fp64 mean stored as fp32), the remainder rounded to bf16; the means re-enter
+    exactly through the intercept coefficient / chain rule, so the effective inputs are mean + bf16(x - mean)."""
+    X = np.asarray(X, dtype=np.float64)
+    c = X.mean(axis=0).astype(np.float32)
+    dev = X.astype(np.float32) - c
+    return c.astype(np.float64) + bf16_round(dev)

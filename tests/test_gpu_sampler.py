@@ -63,21 +63,52 @@ def test_logdensity_parity(model, J, n, D):
 @pytest.mark.parametrize('model', dens.MODELS)
 @pytest.mark.parametrize('n,D', [(37, 3), (128, 8), (700, 19), (5000, 49), (1300, 63)])
 def test_logdensity_parity_tensor_core(model, n, D):
-    """tcgen05/TMA likelihood pass: X is stored in bf16 (a data quantisation, the
-    coefficients stay fp32-accurate through the hi/lo split), so the check is
-    against the fp64 oracle evaluated on the SAME bf16-rounded design matrix.
+    """tcgen05/TMA likelihood pass: X is stored in bf16, centred per site (a data quantisation
+    of the deviations from the column means; the coefficients stay fp32-accurate through the
+    hi/lo split), so the check is against the fp64 oracle evaluated on the SAME stored inputs.
     The gradient carries bf16 rounding of the residuals E (~2^-9 relative)."""
     sites = [synth.make_site(model, n, D, 1, seed=31), synth.make_site(model, n + 77, D, 1, seed=32)]
     ctx = make_ctx(model, sites, use_tc=1)
     rng = np.random.RandomState(2)
     for k, site in enumerate(sites):
-        site_q = dict(site, X=synth.bf16_round(site['X']))
+        site_q = dict(site, X=synth.tc_stored_X(site['X']))
         td = synth.oracle_density(model, site_q)
         q = 0.4 * rng.standard_normal((21, td.p))       # > 16: exercises batching
         lp, grad = ctx.logdensity(k, q)
         olp, ograd = td.lp_grad(q)
         assert np.max(np.abs(lp - olp) / np.maximum(1.0, np.abs(olp))) < 5e-5
         assert np.max(np.abs(grad - ograd)) < 6e-3 * max(1.0, np.max(np.abs(ograd)))
+    ctx.close()
+
+
+def test_tensor_core_pass_keeps_shifted_inputs():
+    """Inputs like 35.5 +- 0.02 (the simulators shift the inputs of groups with extreme intercepts,
+    common.py:132-317): plain bf16 storage (8 significant bits) would erase the within-site variation;
+    the centred copy keeps it -- parity with the fp64 oracle on the TRUE inputs, not only the stored ones."""
+    model, n, D = 'm3b', 2000, 49
+    site = synth.make_site(model, n, D, 1, seed=51)
+    rng = np.random.RandomState(4)
+    site['X'] = 35.5 + 0.02 * rng.standard_normal((n, D))
+    f = 0.3 + (site['X'] - 35.5) @ (20.0 * rng.standard_normal(D))
+    site['y'] = (rng.uniform(size=n) < 1 / (1 + np.exp(-f))).astype(np.int64)
+    ctx = make_ctx(model, [site, site], use_tc=1)
+    td = synth.oracle_density(model, site)
+    td_stored = synth.oracle_density(model, dict(site, X=synth.tc_stored_X(site['X'])))
+    td_plain = synth.oracle_density(model, dict(site, X=synth.bf16_round(site['X'])))
+    q = 0.05 * rng.standard_normal((8, td.p))
+    q[:, td.d + 1:] = 10.0 * rng.standard_normal((8, D))      # slopes that resolve the 0.02 spread
+    q[:, 1:td.d] = 0.1 * rng.standard_normal((8, D))
+    # keep the mean part of the predictor moderate: sum(beta) ~ 0
+    beta = q[:, td.d + 1:] * np.exp(q[:, 1:td.d])
+    q[:, td.d + 1] -= beta.sum(axis=1) / np.exp(q[:, 1])
+    lp, grad = ctx.logdensity(0, q)
+    olp, ograd = td.lp_grad(q)
+    slp, sgrad = td_stored.lp_grad(q)
+    plp, _ = td_plain.lp_grad(q)
+    assert np.max(np.abs(lp - slp) / np.maximum(1.0, np.abs(slp))) < 5e-5
+    assert np.max(np.abs(lp - olp) / np.maximum(1.0, np.abs(olp))) < 2e-3       # true inputs: bf16 of the deviations
+    assert np.max(np.abs(plp - olp) / np.maximum(1.0, np.abs(olp))) > 10 * np.max(np.abs(lp - olp) / np.maximum(1.0, np.abs(olp)))
+    assert np.max(np.abs(grad - sgrad)) < 6e-3 * max(1.0, np.max(np.abs(sgrad)))
     ctx.close()
 
 
