@@ -353,6 +353,7 @@ class Master(object):
         df_select         = None,
         df_min            = None,
         df_snr_z          = 3.0,
+        df_snr_min        = 0.5,
         # extension: a site whose max split-Rhat exceeds this is treated as failed for the iteration
         # (its update is skipped like a failed moment estimate, method.py:460-465); None = never
         rhat_max          = None
@@ -493,6 +494,7 @@ class Master(object):
             self.df0 = lambda i: 1.0              # the selection rule picks below this cap
         self.df_min = min(1.0 / self.K, 0.2) if kwargs['df_min'] is None else float(kwargs['df_min'])
         self.df_snr_z = float(kwargs['df_snr_z'])
+        self.df_snr_min = float(kwargs['df_snr_min'])
         self.rhat_max = kwargs['rhat_max']
         # per-iteration record of the last run(): damping used, update attempts, selection statistics
         self.history = dict(df=[], attempts=[], snr=[], n_ok=[], rhat_sites=[], n_fail=[])
@@ -625,7 +627,14 @@ class Master(object):
         the positive-part shrinkage estimate of the fraction of the summed update that is signal
         (the damping that minimises the expected squared distance to the fixed point).  The
         estimate is taken `df_snr_z` standard errors low, capped by `df0(iter)` and floored at
-        `df_min` (default min(1/K, 0.2), the reference's asymptotic damping, fit.py:176-186)."""
+        `df_min` (default min(1/K, 0.2), the reference's asymptotic damping, fit.py:176-186).
+
+        Below `df_snr_min` (default 0.5: noise power above signal power) the floor is used outright.
+        A small apparent signal fraction is not trustworthy: the unbiased-precision factor
+        (n-d-2) of method.py:431-434 assumes independent Gaussian draws, and a relative bias b of
+        the per-site precision estimate (autocorrelated draws: b ~ (tau-1)/n) is COHERENT over the
+        sites -- it enters the summed update K times and looks like signal.  At the floor 1/K the
+        update is the average of the sites' tilted estimates and such a bias passes through once."""
         ctx = self._shard.ctx
         ctx.delta_sums()
         self._allreduce_device(ctx.dsum_tensor())
@@ -637,7 +646,7 @@ class Master(object):
         if n_ok >= 2 and T2 > 0.0:
             N2 = max(S2 - T2 / n_ok, 0.0) * n_ok / (n_ok - 1.0)
             raw = 1.0 - (1.0 + self.df_snr_z * np.sqrt(2.0 / dof)) * N2 / T2
-        df = min(cap, max(self.df_min, raw))
+        df = min(cap, max(self.df_min, raw)) if raw >= self.df_snr_min else min(cap, self.df_min)
         self.history['snr'].append((T2, N2, raw))
         return df
 
