@@ -355,7 +355,8 @@ def run_ours(args, model, K, n_k, D, chains, siter):
             dist.barrier()
         torch.cuda.synchronize()
 
-    hist = dict(df=[], attempts=[], mrhat=[], mstep=[], stime=[], other=[], m=[], S=[], rhat_sites=[], snr=[], n_fail=[])
+    hist = dict(df=[], attempts=[], mrhat=[], mstep=[], stime=[], other=[], m=[], S=[], rhat_sites=[], snr=[], n_fail=[],
+                rejected=[])
 
     def timed_run(nsteps, per_step_calls=False):
         """nsteps EP iterations: one run(nsteps) call, or nsteps calls of run(1) (the e2e leg: host state in and
@@ -377,6 +378,7 @@ def run_ours(args, model, K, n_k, D, chains, siter):
             hist['rhat_sites'] += list(m.history['rhat_sites'][:n_done])
             hist['snr'] += list(m.history['snr'][:n_done])
             hist['n_fail'] += list(m.history['n_fail'][:n_done])
+            hist['rejected'] += list(m.history['rejected'][:n_done])
             hist['mrhat'] += list(mrh_[:n_done])
             hist['mstep'] += list(mst_[:n_done])
             hist['stime'] += list(st_[:n_done])
@@ -489,6 +491,8 @@ def run_ours(args, model, K, n_k, D, chains, siter):
             'df_used': [round(float(v), 6) for v in hist['df']],
             'update_attempts': [int(v) for v in hist['attempts']],
             'sites_skipped': [int(v) for v in hist['n_fail']],     # failed moment estimate or Rhat > rhat_max
+            # (rank 0's shard) the sites over rhat_max: they restart from a random initialisation next time
+            'sites_rejected_rank0': [[int(k) for k in v] for v in hist['rejected']],
             'max_rhat': [round(float(v), 4) for v in hist['mrhat']],
             'mean_stepsize': [round(float(v), 5) for v in hist['mstep']],
             'sampling_s': [round(float(v), 3) for v in hist['stime']],

@@ -52,6 +52,8 @@ struct epg_site_data {
     float* xmean = nullptr;             // [K][64] per-site column means the bf16 copy is centred on (0 beyond column D-1)
     int* order = nullptr;               // [K] launch order of the sites: most expensive (gradient evaluations of the
     std::vector<double> h_cost;         //     previous run, h_cost) first, so that stragglers do not start last
+    unsigned char* reinit = nullptr;    // [K] 1: the next init_prev run starts this site's chains at random (epg_reinit_sites)
+    std::vector<unsigned char> h_reinit;
     CUtensorMap tmap;                   // TMA descriptor of Xb: box 64 x 128 rows, 128-byte swizzle
     bool tc_ok = false;                 // tensor-core pass usable (single group, D+1 <= 64)
     int use_tc = 1;                     // option (epg_set_option "use_tc")
@@ -81,7 +83,7 @@ struct epg_site_data {
 void epg_sites_free(epg_ctx* c) {
     epg_site_data* s = c->sites;
     if (!s) return;
-    cudaFree(s->xmean); cudaFree(s->order);
+    cudaFree(s->xmean); cudaFree(s->order); cudaFree(s->reinit);
     cudaFree(s->X); cudaFree(s->Xb); cudaFree(s->y); cudaFree(s->row0); cudaFree(s->grp_ptr); cudaFree(s->grp_rows);
     cudaFree(s->chain_mem); cudaFree(s->last_q); cudaFree(s->omega); cudaFree(s->out); cudaFree(s->ld_buf);
     delete s;
@@ -189,6 +191,7 @@ enum { PH_START = 0, PH_START_WAIT, PH_SS_WAIT, PH_TREE_WAIT, PH_DONE, PH_DEAD }
 
 struct ChainS {
     int phase, iter, depth, nleaf, sign, n_leap_tr, ss_dir, ss_first, init_tries, restart_ss;
+    int init_mode;                // SamplerArgs::init_mode, or 0 for a site marked by epg_reinit_sites
     uint32_t rng;
     float eps;
     double V, H0, Vs, lsw, sum_metro, cur_lsw, Vprop;
@@ -210,6 +213,7 @@ struct SamplerArgs {
     const float* X; const float* y; const int64_t* row0; const int* grp_ptr; const int* grp_rows;
     const float* xmean;                // [K][64] column means of the centred bf16 copy (tensor-core pass)
     const int* order;                  // launch order: block b samples site k0 + order[b] (nullptr: identity)
+    const unsigned char* reinit;       // [K] per local site: start the chains at random although init_mode == 2 (nullptr: none)
     int model, D, S, d;
     // cavity
     const double* cavQ; const double* cavm; float* omega;
@@ -1005,15 +1009,15 @@ __device__ void chain_step(const CX& x, ChainS& s, double lp_lik, int c_local, i
             begin_ss_trial(x, s);
             return;
         }
-        if (a.init_mode == 0 && s.init_tries < 100) { s.init_tries++; s.phase = PH_START; }   // redraw below
+        if (s.init_mode == 0 && s.init_tries < 100) { s.init_tries++; s.phase = PH_START; }   // redraw below
         else { s.phase = PH_DEAD; return; }
     }
     if (s.phase == PH_START) {
         float* q = x.v(V_Q);
-        if (a.init_mode == 2) {
+        if (s.init_mode == 2) {
             const float* lq = a.last_q + (size_t)x.cg * a.P;
             for (int i = x.lane; i < x.p; i += 32) q[i] = lq[i];
-        } else if (a.init_mode == 1) {
+        } else if (s.init_mode == 1) {
             for (int i = x.lane; i < x.p; i += 32) q[i] = 0.0f;
         } else {
             const uint32_t ctr = s.rng++;
@@ -1170,6 +1174,7 @@ __device__ __forceinline__ void init_chains(const SamplerArgs& a, const SiteView
         if (lane == 0) {
             memset(&s, 0, sizeof(ChainS));
             s.phase = PH_START;
+            s.init_mode = (a.init_mode == 2 && a.reinit && a.reinit[sv.k]) ? 0 : a.init_mode;
             s.eps = 1.0f;
             s.mu = log(10.0);
             s.rng = 0;
@@ -1895,6 +1900,15 @@ int epg_tilted_sample(epg_ctx* c, int k0, int k1, const uint32_t* seeds, const e
         EPG_CHECK(c, cudaStreamSynchronize(c->stream));           // (ord is a local)
         a.order = s->order;
     }
+    // sites marked by epg_reinit_sites: random starting points instead of the previous last draws (consumed here)
+    if (o->init_mode == 2 && (int)s->h_reinit.size() == c->K &&
+        std::any_of(s->h_reinit.begin() + k0, s->h_reinit.begin() + k1, [](unsigned char f) { return f != 0; })) {
+        if (!s->reinit) EPG_CHECK(c, cudaMalloc((void**)&s->reinit, (size_t)c->K));
+        EPG_CHECK(c, cudaMemcpyAsync(s->reinit, s->h_reinit.data(), (size_t)c->K, cudaMemcpyHostToDevice, c->stream));
+        EPG_CHECK(c, cudaStreamSynchronize(c->stream));
+        a.reinit = s->reinit;
+    }
+    if ((int)s->h_reinit.size() == c->K) std::fill(s->h_reinit.begin() + k0, s->h_reinit.begin() + k1, (unsigned char)0);
 #ifdef EPG_TC_EXPERIMENT
     { int kn = getenv("EPGPU_KNOBS") ? atoi(getenv("EPGPU_KNOBS")) : 0; cudaMemcpyToSymbol(tc::g_knobs, &kn, sizeof(int)); }
 #endif
@@ -1971,6 +1985,17 @@ int epg_tilted_sample(epg_ctx* c, int k0, int k1, const uint32_t* seeds, const e
         for (int i = 0; i < k1 - k0; ++i) { cc += out[8 * i + 4]; cl += out[8 * i + 5]; nt += out[8 * i + 6]; }
         fprintf(stderr, "[epgpu] sampler %d sites: %.3f s, ticks/site %.0f, cycles/tick chain %.0f lik %.0f (tc=%d pp=%d nst=%d levels=%d smem=%zu)\n",
                 k1 - k0, ms * 1e-3, nt / (k1 - k0), cc / nt, cl / nt, a.use_tc, a.pp, a.tc_nst, a.hot_levels, a.smem_total);
+    }
+    return 0;
+}
+
+int epg_reinit_sites(epg_ctx* c, int n, const int32_t* sites) {
+    if (!c->sites || n < 0 || (n > 0 && !sites)) return epg_fail_msg(c, "epg_reinit_sites: bad args / no site data");
+    epg_site_data* s = c->sites;
+    if ((int)s->h_reinit.size() != c->K) s->h_reinit.assign((size_t)c->K, 0);
+    for (int i = 0; i < n; ++i) {
+        if (sites[i] < 0 || sites[i] >= c->K) return epg_fail_msg(c, "epg_reinit_sites: bad site index");
+        s->h_reinit[sites[i]] = 1;
     }
     return 0;
 }

@@ -52,6 +52,7 @@ SYMBOLS = [
     ('epg_get_draws', C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, _c_double_p]),
     ('epg_moments', C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, _c_int32_p, C.POINTER(C.c_int)]),
     ('epg_fail_sites', C.c_int, [C.c_void_p, C.c_int, _c_int32_p]),
+    ('epg_reinit_sites', C.c_int, [C.c_void_p, C.c_int, _c_int32_p]),
     ('epg_update_partial', C.c_int, [C.c_void_p, C.c_double]),
     ('epg_update_finish', C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
     ('epg_accept', C.c_int, [C.c_void_p]),
@@ -239,6 +240,10 @@ class Context:
     def fail_sites(self, sites):
         sites = np.ascontiguousarray(sites, dtype=np.int32)
         self._ck(self._lib.epg_fail_sites(self._h, len(sites), sites.ctypes.data_as(_c_int32_p)))
+
+    def reinit_sites(self, sites):
+        sites = np.ascontiguousarray(sites, dtype=np.int32)
+        self._ck(self._lib.epg_reinit_sites(self._h, len(sites), sites.ctypes.data_as(_c_int32_p)))
 
     def update_partial(self, df):
         self._ck(self._lib.epg_update_partial(self._h, float(df)))

@@ -497,7 +497,8 @@ class Master(object):
         self.df_snr_min = float(kwargs['df_snr_min'])
         self.rhat_max = kwargs['rhat_max']
         # per-iteration record of the last run(): damping used, update attempts, selection statistics
-        self.history = dict(df=[], attempts=[], snr=[], n_ok=[], rhat_sites=[], n_fail=[])
+        self.history = dict(df=[], attempts=[], snr=[], n_ok=[], rhat_sites=[], n_fail=[], rejected=[])
+        self._last_rejected = []
 
         # host mirrors (reference method.py:836-851), F-order as the reference
         self.S = np.empty((d, d), order='F')
@@ -728,6 +729,11 @@ class Master(object):
             if bad:
                 ctx.fail_sites(bad)
                 oks[bad] = False
+                if self.builtin:
+                    # init_prev would restart the chains where they got stuck: next time these sites
+                    # start from Stan's random initialisation instead
+                    ctx.reinit_sites(bad)
+            self._last_rejected = [sh.k_begin + i for i in bad]
         for w, ok in zip(workers, oks):
             w.nsamp = n
             if w._mode_now() == 'sample' and w.prec_estim_skip > 0:
@@ -790,7 +796,7 @@ class Master(object):
                 # first instead of overwriting the device with the stale host copies
                 self._pull_state()
             self._push_state(with_cavity=True)
-        self.history = dict(df=[], attempts=[], snr=[], n_ok=[], rhat_sites=[], n_fail=[])
+        self.history = dict(df=[], attempts=[], snr=[], n_ok=[], rhat_sites=[], n_fail=[], rejected=[])
         local_workers = self.workers[sh.k_begin:sh.k_end]
 
         for cur_iter in range(niter):
@@ -820,6 +826,7 @@ class Master(object):
             # distribution of the per-site max split-Rhat behind that maximum (local shard)
             rh = np.array([w.last_mrhat for w in local_workers if w.last_mrhat is not None], dtype=np.float64)
             rh = rh[np.isfinite(rh)]
+            self.history['rejected'].append(list(self._last_rejected))   # (local shard) sites over rhat_max
             self.history['rhat_sites'].append(
                 (float(np.median(rh)), float(np.percentile(rh, 90)), float(np.mean(rh > 1.1))) if rh.size
                 else (float('nan'),) * 3)

@@ -197,6 +197,12 @@ int epg_tilted_sample(epg_ctx* ctx, int k0, int k1, const uint32_t* seeds,
                       const epg_sampler_opts* opts, double* msteps_out, double* mrhat_out,
                       int64_t* n_leapfrog_out, double* seconds);
 
+/* Marks local sites whose chains the next epg_tilted_sample with init_mode 2 starts from Stan's random
+ * initialisation U(-2,2) instead of their previous last draws (an extension: with init_prev,
+ * method.py:404-406, a chain that got stuck -- e.g. in a funnel neck with a collapsed step size -- would
+ * otherwise stay stuck for the rest of the EP run).  The marks are consumed by that call. */
+int epg_reinit_sites(epg_ctx* ctx, int n, const int32_t* sites);
+
 /* Options.  "use_tc" (default 1): use the tcgen05/TMA likelihood pass when the
  * shapes allow it (single-group sites, D+1 <= 64, chains <= 16); 0 forces the
  * fp32 SIMT pass.  "pingpong" (default 0): 1 = with the tensor-core pass, more

@@ -123,6 +123,9 @@ class OracleContext(object):
             self.a[DRI][:, k] = 0.0
             self._ok[k] = False
 
+    def reinit_sites(self, sites):
+        self.reinit_marks = getattr(self, 'reinit_marks', []) + [int(k) for k in sites]
+
     def update_partial(self, df):
         self.a[QI2][...] = self.a[QI] + df * self.a[DQI]
         self.a[RI2][...] = self.a[RI] + df * self.a[DRI]
