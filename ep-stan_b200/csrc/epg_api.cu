@@ -96,6 +96,7 @@ void epg_destroy(epg_ctx* c) {
     if (c->scratch) cudaFree(c->scratch);
     if (c->util_buf) cudaFree(c->util_buf);
     if (c->snr_buf) cudaFree(c->snr_buf);
+    if (c->mom_buf) cudaFree(c->mom_buf);
     if (c->h_flags) cudaFreeHost(c->h_flags);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;

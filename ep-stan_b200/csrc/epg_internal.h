@@ -36,6 +36,10 @@ struct epg_ctx {
     double* util_buf = nullptr;
     size_t util_bytes = 0;
 
+    // per-site packed Gram + shift between the two moment-matching kernels (epg_moments.cu)
+    double* mom_buf = nullptr;
+    size_t mom_bytes = 0;
+
     // scratch of the damping-selection statistics (epg_snr.cu)
     double* snr_buf = nullptr;
     size_t snr_bytes = 0;

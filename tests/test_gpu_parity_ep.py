@@ -1,0 +1,75 @@
+"""Posterior parity, north_star check (c), on BASELINE shapes (VERDICT r1 "next" item 2).
+
+The GPU EP run (batched NUTS on the tcgen05 pass + fp64 moment matching / updates) against
+  (i)  the oracle EP run on the SAME data with the same seed-independent settings (oracle NUTS per site,
+       oracle moment matching and updates; tests/oracle_refs_ep.py, cached in tests/golden/ep_ref_<tag>.npz);
+  (ii) the full-data posterior of phi sampled by the oracle NUTS ("target", what fit.py --run_target does).
+Tolerances are KL divergences between the Gaussian approximations, stated per assertion: both EP runs carry
+Monte Carlo noise from C x 100 draws per site and iteration, the target from 8 x 500 draws.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import ep_linalg as orc
+import oracle_refs_ep as refs
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+
+
+def _ref(tag):
+    path = os.path.join(GOLD, 'ep_ref_%s.npz' % tag)
+    if not os.path.exists(path):
+        pytest.skip('no cached oracle reference %s (python tests/oracle_refs_ep.py %s)' % (path, tag))
+    return np.load(path)
+
+
+def _gpu_ep(tag):
+    import epstan.method as method
+    model, Ktot, K, n_k, D, C, siter, niter = refs.CASES[tag]
+    X, y, prior = refs.problem(tag)
+    m = method.Master('experiment/models/%s_sg' % model, X, y, site_sizes=np.full(K, n_k), prior=prior,
+                      chains=C, iter=siter, df0=orc.default_df0(K), df_select='snr')
+    info, (ms, Ss), (st, mst, mrh, oth) = m.run(niter, verbose=False, seed=4321, return_analytics=True)
+    assert info == 0
+    return m, ms, Ss, mrh
+
+
+def test_cfg3_ep_vs_oracle_ep_and_target():
+    """BASELINE configs[2]: m1b_sg, K=64, n_k=2000, D=19 (d=20), 8 chains x 200, 12 EP iterations."""
+    ref = _ref('cfg3')
+    m, ms, Ss, mrh = _gpu_ep('cfg3')
+    d = ms.shape[1]
+    # (i) same algorithm, different sampler implementation and seeds
+    kl_ep = orc.kl_mvn(ref['ep_m'][-1], ref['ep_S'][-1], ms[-1], Ss[-1])
+    # (ii) against the full-data posterior
+    kl_tgt = orc.kl_mvn(ref['tgt_m'], ref['tgt_S'], ms[-1], Ss[-1])
+    kl_tgt_oracle = orc.kl_mvn(ref['tgt_m'], ref['tgt_S'], ref['ep_m'][-1], ref['ep_S'][-1])
+    sd = np.sqrt(np.diag(ref['tgt_S']))
+    z = np.abs(ms[-1] - ref['tgt_m']) / sd
+    print('cfg3: KL(oracle EP || GPU EP) %.4f  KL(target || GPU EP) %.4f  KL(target || oracle EP) %.4f  '
+          'max |mean - target| / sd %.3f  max Rhat last iteration %.3f  df %s' % (
+              kl_ep, kl_tgt, kl_tgt_oracle, z.max(), mrh[-1], np.round(m.history['df'], 4)))
+    assert kl_ep < 0.5, kl_ep                      # d = 20: 0.5 nat ~ a quarter of a posterior sd per dimension
+    assert kl_tgt < max(1.0, 2.0 * kl_tgt_oracle), (kl_tgt, kl_tgt_oracle)
+    assert z.max() < 1.0
+    assert np.all(mrh[3:] < 1.2), mrh
+    # the run has settled: successive global approximations differ by less than the noise of one iteration
+    step = [orc.kl_mvn(ms[i], Ss[i], ms[i - 1], Ss[i - 1]) for i in range(1, len(ms))]
+    assert max(step[-3:]) < 0.2, step
+
+
+def test_cfg4_subset_ep_vs_oracle_ep():
+    """First 32 sites of BASELINE configs[3]: m3b_sg, n_k=5000, D=49 (d=50, 100 sampled parameters per site),
+    4 chains x 200, 8 EP iterations."""
+    ref = _ref('cfg4s')
+    m, ms, Ss, mrh = _gpu_ep('cfg4s')
+    kl_ep = orc.kl_mvn(ref['ep_m'][-1], ref['ep_S'][-1], ms[-1], Ss[-1])
+    sd = np.sqrt(np.diag(ref['ep_S'][-1]))
+    z = np.abs(ms[-1] - ref['ep_m'][-1]) / sd
+    print('cfg4s: KL(oracle EP || GPU EP) %.4f  max |mean diff| / sd %.3f  max Rhat %s  df %s' % (
+        kl_ep, z.max(), np.round(mrh, 3), np.round(m.history['df'], 4)))
+    assert kl_ep < 1.5, kl_ep                      # d = 50
+    assert z.max() < 1.0

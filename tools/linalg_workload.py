@@ -72,6 +72,9 @@ if timing:
     res['update_partial'] = (timed(lambda: ctx.update_partial(0.5 / K)), 8.0 * 3 * K * (d * d + d))
     res['cavity'] = (timed(lambda: ctx.cavity(proposal=True)), 8.0 * K * (2 * d * d + 2 * d + d * d + d))
     print('shape K=%d d=%d n=%d  (HBM peak %.0f GB/s measured)' % (K, d, n, peaks['hbm_gbs']))
+    # algorithmic fp64 flop per site: moments 2 n d^2 + 7/3 d^3, cavity 1/3 d^3 + 2 d^2 (x2: FMA = 2 flop)
+    flops = {'moments_sample': K * (2.0 * n * d * d + 7.0 / 3.0 * d ** 3), 'moments_olse': K * (2.0 * n * d * d + 7.0 / 3.0 * d ** 3),
+             'cavity': K * (2.0 / 3.0 * d ** 3 + 4.0 * d * d), 'update_partial': 2.0 * K * (d * d + d)}
     for name, (t, byt) in res.items():
-        print('  %-16s %9.1f us   algorithmic %8.2f MB   %7.1f GB/s   %5.1f %% of HBM peak'
-              % (name, t * 1e6, byt / 1e6, byt / t / 1e9, 100 * byt / t / 1e9 / peaks['hbm_gbs']))
+        print('  %-16s %9.1f us   algorithmic %8.2f MB   %7.1f GB/s   %5.1f %% of HBM peak   %6.2f fp64 TFLOP/s'
+              % (name, t * 1e6, byt / 1e6, byt / t / 1e9, 100 * byt / t / 1e9 / peaks['hbm_gbs'], flops[name] / t / 1e12))
