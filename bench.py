@@ -342,6 +342,8 @@ def run_ours(args, model, K, n_k, D, chains, siter):
             kw['df0'] = None                   # no cap: the selection may take a full step
     if args.rhat_max > 0:
         kw['rhat_max'] = args.rhat_max
+    if args.no_adapt_prev:
+        kw['adapt_prev'] = False
     m = method.Master('experiment/models/%s_sg' % model, X, y, site_sizes=np.full(K, n_k), prior=prior,
                       chains=chains, iter=siter, **kw)
     n_sample = min(K, max(os.cpu_count() or 1, 2))
@@ -466,6 +468,9 @@ def run_ours(args, model, K, n_k, D, chains, siter):
                                'auto1': 'automatic selection (df_select=snr), no cap',
                                'schedule': 'fit.py default_df0'}[args.damp],
                    'rhat_max': args.rhat_max if args.rhat_max > 0 else None,
+                   'warmup_start': ("Stan defaults (unit metric, step size 1) every EP iteration" if args.no_adapt_prev else
+                                    "init_prev carries the last draw AND the adapted metric / step size of each chain "
+                                    "(adapt_prev=True, an extension; --no-adapt-prev for Stan's defaults)"),
                    'l2': ('inputs larger than L2 (X %.0f MB fp32 + bf16 per GPU)' if x_bytes > 126e6
                           else 'inputs smaller than L2 (X %.0f MB fp32 + bf16 per GPU); not flushed: a step re-reads '
                                'each site\'s X thousands of times by design, the first touch is <0.1 %% of a step')
@@ -524,6 +529,8 @@ def main():
     ap.add_argument('--data', default=None, choices=['sim', 'synth'])
     ap.add_argument('--rhat-max', type=float, default=2.0,
                     help='skip the update of sites whose max split-Rhat exceeds this (0: never, the reference)')
+    ap.add_argument('--no-adapt-prev', action='store_true',
+                    help="Stan's unit metric / step size 1 at the start of every warm-up (the reference's behaviour)")
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
     model, K, n_k, D, chains, siter = WORKLOADS[args.workload]

@@ -21,7 +21,7 @@ size_t epg_array_elems(const epg_ctx* c, int a) {
         case EPG_Q: case EPG_Q0: case EPG_S: return d * d;
         case EPG_R: case EPG_R0: case EPG_M: return d;
         case EPG_PARTIAL: return d * d + d + 1;
-        case EPG_DSUM: return d * d + d + 2;
+        case EPG_DSUM: return d * d + d + 2 + EPG_XCHG_SLOTS;
         default: return 0;
     }
 }
@@ -97,6 +97,7 @@ void epg_destroy(epg_ctx* c) {
     if (c->util_buf) cudaFree(c->util_buf);
     if (c->snr_buf) cudaFree(c->snr_buf);
     if (c->mom_buf) cudaFree(c->mom_buf);
+    if (c->q_prev) cudaFree(c->q_prev);
     if (c->h_flags) cudaFreeHost(c->h_flags);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -156,6 +157,12 @@ int epg_download(epg_ctx* c, int a, int k0, int k1, double* host) {
     EPG_CHECK(c, cudaMemcpyAsync(host, c->arr[a] + off, sizeof(double) * cnt, cudaMemcpyDeviceToHost, c->stream));
     EPG_CHECK(c, cudaStreamSynchronize(c->stream));
     return 0;
+}
+
+int64_t epg_array_count(epg_ctx* c, int a, int k0, int k1) {
+    if (!c || a < 0 || a >= EPG_NARRAYS) return -1;
+    const size_t st = epg_array_site_stride(c, a);
+    return (int64_t)(st ? st * (size_t)(k1 - k0) : epg_array_elems(c, a));
 }
 
 void* epg_device_ptr(epg_ctx* c, int a) {

@@ -40,6 +40,11 @@ struct epg_ctx {
     double* mom_buf = nullptr;
     size_t mom_bytes = 0;
 
+    // global (Q, r) at the time of the last epg_delta_sums: base of epg_update_from_sums
+    double* q_prev = nullptr;
+    size_t q_prev_bytes = 0;
+    bool q_prev_valid = false;
+
     // scratch of the damping-selection statistics (epg_snr.cu)
     double* snr_buf = nullptr;
     size_t snr_bytes = 0;

@@ -57,6 +57,7 @@ struct epg_site_data {
     CUtensorMap tmap;                   // TMA descriptor of Xb: box 64 x 128 rows, 128-byte swizzle
     bool tc_ok = false;                 // tensor-core pass usable (single group, D+1 <= 64)
     int use_tc = 1;                     // option (epg_set_option "use_tc")
+    int carry_adapt = 1;                // option "carry_adapt": init_prev runs start from the previous run's adapted metric / step size
     int pp_mode = 0;                    // option "pingpong": 0 never (default), 1 when sites > SMs and L2-resident, 2 always
     float* y = nullptr;                 // [N]
     int64_t* row0 = nullptr;            // [K+1]
@@ -191,7 +192,7 @@ enum { PH_START = 0, PH_START_WAIT, PH_SS_WAIT, PH_TREE_WAIT, PH_DONE, PH_DEAD }
 
 struct ChainS {
     int phase, iter, depth, nleaf, sign, n_leap_tr, ss_dir, ss_first, init_tries, restart_ss;
-    int init_mode;                // SamplerArgs::init_mode, or 0 for a site marked by epg_reinit_sites
+    int init_mode;                // SamplerArgs::init_mode, or 3 (around the cavity mean) for a site marked by epg_reinit_sites
     uint32_t rng;
     float eps;
     double V, H0, Vs, lsw, sum_metro, cur_lsw, Vprop;
@@ -219,6 +220,8 @@ struct SamplerArgs {
     const double* cavQ; const double* cavm; float* omega;
     // chains
     float* chain_mem; float* last_q; int P, C;
+    float* last_minv; float* last_eps;  // [K*C][P], [K*C]: adapted metric / step size at the end of the previous run
+    int carry_adapt;                    // init_prev also starts the warm-up from them (option "carry_adapt")
     int iter, warmup, init_mode, max_depth;
     double delta;
     int win_init, win_term, win_base;
@@ -973,7 +976,10 @@ __device__ void end_transition(const CX& x, ChainS& s, int c_local, int k_global
     }
     if (s.iter >= a.iter) {
         float* lq = a.last_q + (size_t)x.cg * a.P;
-        for (int i = x.lane; i < x.p; i += 32) lq[i] = qs[i];
+        float* lm = a.last_minv + (size_t)x.cg * a.P;
+        const float* minv = x.v(V_MINV);
+        for (int i = x.lane; i < x.p; i += 32) { lq[i] = qs[i]; lm[i] = minv[i]; }
+        if (x.lane == 0) a.last_eps[x.cg] = s.eps;
         s.phase = PH_DONE;
         return;
     }
@@ -1009,7 +1015,7 @@ __device__ void chain_step(const CX& x, ChainS& s, double lp_lik, int c_local, i
             begin_ss_trial(x, s);
             return;
         }
-        if (s.init_mode == 0 && s.init_tries < 100) { s.init_tries++; s.phase = PH_START; }   // redraw below
+        if ((s.init_mode == 0 || s.init_mode == 3) && s.init_tries < 100) { s.init_tries++; s.phase = PH_START; }   // redraw below
         else { s.phase = PH_DEAD; return; }
     }
     if (s.phase == PH_START) {
@@ -1019,6 +1025,16 @@ __device__ void chain_step(const CX& x, ChainS& s, double lp_lik, int c_local, i
             for (int i = x.lane; i < x.p; i += 32) q[i] = lq[i];
         } else if (s.init_mode == 1) {
             for (int i = x.lane; i < x.p; i += 32) q[i] = 0.0f;
+        } else if (s.init_mode == 3) {
+            // re-initialisation of a site whose chains did not mix: phi within one conditional cavity standard
+            // deviation of the cavity mean, latents in U(-1, 1).  (Late in an EP run the cavity is so tight that
+            // Stan's U(-2, 2) starts thousands of standard deviations out and the step size collapses.)
+            const uint32_t ctr = s.rng++;
+            for (int i = x.lane; i < x.p; i += 32) {
+                const uint4 r = philox4x32(make_uint4(ctr, (uint32_t)i, 5u, 0u), x.key);
+                const float u = 2.0f * u01(r.x) - 1.0f;
+                q[i] = i < x.d ? x.muf()[i] + u * rsqrtf(fmaxf(x.omega[i * x.d + i], 1e-12f)) : u;
+            }
         } else {
             const uint32_t ctr = s.rng++;
             for (int i = x.lane; i < x.p; i += 32) {
@@ -1169,21 +1185,41 @@ __device__ __forceinline__ void load_cavity(const SamplerArgs& a, int k, float* 
 
 // initial state of the site's chains; warp w of a group of nw warps
 __device__ __forceinline__ void init_chains(const SamplerArgs& a, const SiteView& sv, ChainS* cs, int w, int nw, int lane) {
+    const int im = (a.init_mode == 2 && a.reinit && a.reinit[sv.k]) ? 3 : a.init_mode;
     for (int c = w; c < a.C; c += nw) {
         ChainS& s = cs[c];
+        const int cg = sv.k * a.C + c;
+        // Warm-up starting point.  Stan: unit metric, step size 1.  With init_prev (method.py:404-406 carries the
+        // last draw over) the previous run's ADAPTED metric and step size are carried over as well: the tilted
+        // distribution of a site changes little between EP iterations, while a unit metric makes the first
+        // 90 % of every warm-up crawl at the scale of the tightest cavity direction with saturated trees.
+        // A re-initialised site (mode 3) starts from the conditional cavity variances instead.
+        float eps0 = 1.0f;
+        if (im == 2 && a.carry_adapt) {
+            const float e = a.last_eps[cg];
+            if (e > 0.0f && isfinite(e)) eps0 = e;
+        }
         if (lane == 0) {
             memset(&s, 0, sizeof(ChainS));
             s.phase = PH_START;
-            s.init_mode = (a.init_mode == 2 && a.reinit && a.reinit[sv.k]) ? 0 : a.init_mode;
-            s.eps = 1.0f;
-            s.mu = log(10.0);
+            s.init_mode = im;
+            s.eps = eps0;
+            s.mu = log(10.0 * (double)eps0);
             s.rng = 0;
             s.win_next = a.win_init + a.win_base - 1;
             s.win_size = a.win_base;
         }
         const int vecs[] = {V_WMEAN, V_WM2, V_RS0, V_RQ0, V_RS1, V_RQ1};
         for (int i = lane; i < a.P; i += 32) {
-            cvec(a, sv, c, V_MINV)[i] = 1.0f;
+            float mv = 1.0f;
+            if (im == 2 && a.carry_adapt) {
+                const float v = a.last_minv[(size_t)cg * a.P + i];
+                if (v > 0.0f && isfinite(v)) mv = v;
+            } else if (im == 3 && i < a.d) {
+                const double om = a.cavQ[(size_t)sv.k * a.d * a.d + (size_t)i * a.d + i];
+                if (om > 0.0 && isfinite(om)) mv = (float)(1.0 / om);
+            }
+            cvec(a, sv, c, V_MINV)[i] = mv;
             for (int v = 0; v < 6; ++v) cvec(a, sv, c, vecs[v])[i] = 0.0f;
         }
     }
@@ -1782,6 +1818,11 @@ int epg_set_option(epg_ctx* c, const char* name, double value) {
         c->sites->use_tc = value != 0.0;
         return 0;
     }
+    if (strcmp(name, "carry_adapt") == 0) {
+        if (!c->sites) return epg_fail_msg(c, "epg_set_option(carry_adapt): upload the sites first");
+        c->sites->carry_adapt = value != 0.0;
+        return 0;
+    }
     if (strcmp(name, "pingpong") == 0) {
         if (!c->sites) return epg_fail_msg(c, "epg_set_option(pingpong): upload the sites first");
         c->sites->pp_mode = (int)value;
@@ -1809,7 +1850,8 @@ static int fill_args(epg_ctx* c, SamplerArgs& a, int C, int CP, int n_sites = 1,
         EPG_CHECK(c, cudaMalloc((void**)&s->chain_mem, need));
         s->chain_mem_bytes = need;
     }
-    const size_t need_lq = sizeof(float) * (size_t)c->K * C * s->Pmax;
+    const size_t n_lq = (size_t)c->K * C * s->Pmax;               // last_q | last_minv | last_eps
+    const size_t need_lq = sizeof(float) * (2 * n_lq + (size_t)c->K * C);
     if (need_lq > s->last_q_bytes || s->last_C != C) {
         if (s->last_q) cudaFree(s->last_q);
         s->last_q = nullptr; s->last_q_bytes = 0;
@@ -1820,6 +1862,7 @@ static int fill_args(epg_ctx* c, SamplerArgs& a, int C, int CP, int n_sites = 1,
     EPG_CHECK(c, epg_reserve((void**)&s->omega, &s->omega_bytes, sizeof(float) * (size_t)c->K * (c->d * c->d + c->d)));
     EPG_CHECK(c, epg_reserve((void**)&s->out, &s->out_bytes, sizeof(double) * (size_t)c->K * 8 + sizeof(uint32_t) * ((size_t)c->K + 4)));
     a.chain_mem = s->chain_mem; a.last_q = s->last_q; a.omega = s->omega; a.out = s->out;
+    a.last_minv = s->last_q + n_lq; a.last_eps = s->last_q + 2 * n_lq; a.carry_adapt = s->carry_adapt;
     a.use_tc = (s->tc_ok && s->use_tc && C <= tc::NCH) ? 1 : 0;
     // More sites than SMs: the ping-pong kernel (two sites per persistent CTA) if both per-site blocks fit.
     a.tc_nst = tc::NST;

@@ -200,8 +200,11 @@ int launch_norms(epg_ctx* c, const SnrPlan& p, const double* dQ, const double* d
 
 extern "C" {
 
-int epg_delta_sums(epg_ctx* c) {
+int epg_delta_sums(epg_ctx* c) { return epg_delta_sums_ex(c, 1, nullptr, 0); }
+
+int epg_delta_sums_ex(epg_ctx* c, int with_norms, const double* slots, int n_slots) {
     if (!c->arr[EPG_Q]) return epg_fail_msg(c, "state not initialised");
+    if (n_slots < 0 || n_slots > EPG_XCHG_SLOTS || (n_slots > 0 && !slots)) return epg_fail_msg(c, "epg_delta_sums_ex: bad slots");
     const int d = c->d, K = c->K;
     const size_t dd = (size_t)d * d;
     const SnrPlan p = snr_plan(K, d);
@@ -213,9 +216,24 @@ int epg_delta_sums(epg_ctx* c) {
     k_fisher_prep<<<1, d <= 32 ? 64 : (d <= 64 ? 128 : (d <= 128 ? 256 : 512)), psm, c->stream>>>(
         c->arr[EPG_Q], c->arr[EPG_R], buf + p.o_L, buf + p.o_m, flag, d);
     SNR_LAUNCH_CHECK(c);
-    if (int rc = launch_norms(c, p, c->arr[EPG_DQI], c->arr[EPG_DRI], buf + p.o_norm, K)) return rc;
-    // DSUM = [sum dQi | sum dri | sum |delta_k|^2 | n_ok]   (failed sites hold zero deltas: method.py:460-465)
+    if (with_norms) {
+        if (int rc = launch_norms(c, p, c->arr[EPG_DQI], c->arr[EPG_DRI], buf + p.o_norm, K)) return rc;
+    } else {
+        EPG_CHECK(c, cudaMemsetAsync(buf + p.o_norm, 0, sizeof(double) * (size_t)K, c->stream));
+    }
+    // the global (Q, r) these deltas refer to: epg_update_from_sums builds its proposals on them
+    EPG_CHECK(c, epg_reserve((void**)&c->q_prev, &c->q_prev_bytes, sizeof(double) * (dd + d)));
+    EPG_CHECK(c, cudaMemcpyAsync(c->q_prev, c->arr[EPG_Q], sizeof(double) * dd, cudaMemcpyDeviceToDevice, c->stream));
+    EPG_CHECK(c, cudaMemcpyAsync(c->q_prev + dd, c->arr[EPG_R], sizeof(double) * d, cudaMemcpyDeviceToDevice, c->stream));
+    c->q_prev_valid = true;
+    // DSUM = [sum dQi | sum dri | sum |delta_k|^2 | n_ok | slots]   (failed sites hold zero deltas: method.py:460-465)
     double* dsum = c->arr[EPG_DSUM];
+    {
+        double h[EPG_XCHG_SLOTS];
+        for (int i = 0; i < EPG_XCHG_SLOTS; ++i) h[i] = i < n_slots ? slots[i] : 0.0;
+        EPG_CHECK(c, cudaMemcpyAsync(dsum + dd + d + 2, h, sizeof(h), cudaMemcpyHostToDevice, c->stream));
+        EPG_CHECK(c, cudaStreamSynchronize(c->stream));             // (h is a local)
+    }
     dim3 grid((unsigned)((dd + 255) / 256), p.nchunks);
     k_site_sum_partial2<<<grid, 256, 0, c->stream>>>(c->arr[EPG_DQI], buf + p.o_part, K, (int)dd, p.ks);
     SNR_LAUNCH_CHECK(c);
@@ -247,6 +265,27 @@ int epg_delta_snr(epg_ctx* c, double* stats_out) {
     EPG_CHECK(c, cudaStreamSynchronize(c->stream));
     if (!hf) return epg_fail_msg(c, "epg_delta_snr: the current global precision is not pos.def.");
     if (stats_out) { stats_out[0] = h[0]; stats_out[1] = h[1]; stats_out[2] = h[2]; }
+    return 0;
+}
+
+// PARTIAL <- (Q_prev - Q0) + df * sum_k dQi  |  (r_prev - r0) + df * sum_k dri : what epg_update_finish adds to
+// the prior, i.e. the proposal Q_prev + df * (summed site deltas), with no further exchange between the ranks
+__global__ void k_partial_from_sums(const double* __restrict__ qprev, const double* __restrict__ Q0,
+                                    const double* __restrict__ r0, const double* __restrict__ dsum,
+                                    double* __restrict__ partial, double df, int d) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    const int dd = d * d;
+    if (e >= dd + d) return;
+    const double base = e < dd ? qprev[e] - Q0[e] : qprev[e] - r0[e - dd];
+    partial[e] = base + df * dsum[e];
+}
+
+int epg_update_from_sums(epg_ctx* c, double df) {
+    if (!c->arr[EPG_Q] || !c->q_prev_valid) return epg_fail_msg(c, "epg_update_from_sums: call epg_delta_sums(_ex) first");
+    const int d = c->d, E = d * d + d;
+    k_partial_from_sums<<<(E + 255) / 256, 256, 0, c->stream>>>(c->q_prev, c->arr[EPG_Q0], c->arr[EPG_R0],
+                                                               c->arr[EPG_DSUM], c->arr[EPG_PARTIAL], df, d);
+    SNR_LAUNCH_CHECK(c);
     return 0;
 }
 

@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(os.path.dirname(_HERE), 'libepgpu.so')
 
 # enum epg_array
 (Q, R, Q0, R0, QI, RI, QI2, RI2, DQI, DRI, CAVQ, CAVM, S, M, PARTIAL, TMEAN, DSUM) = range(17)
+XCHG_SLOTS = 64           # EPG_XCHG_SLOTS: caller-defined doubles at the end of DSUM
 MODEL_IDS = {'m1b': 1, 'm2b': 2, 'm3b': 3, 'm4b': 4, 'm5b': 5}
 PREC_ESTIM = {'sample': 0, 'olse': 1}
 
@@ -46,6 +47,7 @@ SYMBOLS = [
     ('epg_init_state', C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     ('epg_upload', C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, _c_double_p]),
     ('epg_download', C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, _c_double_p]),
+    ('epg_array_count', C.c_int64, [C.c_void_p, C.c_int, C.c_int, C.c_int]),
     ('epg_device_ptr', C.c_void_p, [C.c_void_p, C.c_int]),
     ('epg_cavity', C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, _c_int32_p, C.POINTER(C.c_int)]),
     ('epg_set_draws', C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, _c_double_p]),
@@ -60,6 +62,8 @@ SYMBOLS = [
     ('epg_force_pd', C.c_int, [C.c_void_p, C.c_double, C.c_double, _c_int32_p, _c_double_p]),
     ('epg_delta_sums', C.c_int, [C.c_void_p]),
     ('epg_delta_snr', C.c_int, [C.c_void_p, _c_double_p]),
+    ('epg_delta_sums_ex', C.c_int, [C.c_void_p, C.c_int, _c_double_p, C.c_int]),
+    ('epg_update_from_sums', C.c_int, [C.c_void_p, C.c_double]),
     ('epg_damp_sweep', C.c_int, [C.c_void_p, C.c_int, _c_double_p, _c_double_p, _c_double_p,
                                  _c_double_p, _c_double_p]),
     ('epg_invert_normal_params', C.c_int, [C.c_void_p, C.c_int, C.c_int, _c_double_p, _c_double_p, C.c_int,
@@ -153,13 +157,20 @@ class Context:
     def upload(self, array, host, k0=0, k1=None):
         host = _f64(host, 'F')
         k1 = self.K if k1 is None else k1
+        self._check_count(array, k0, k1, host)
         self._ck(self._lib.epg_upload(self._h, array, k0, k1, _dp(host)))
 
     def download(self, array, out, k0=0, k1=None):
         assert out.dtype == np.float64 and (out.flags.f_contiguous or out.flags.c_contiguous)
         k1 = self.K if k1 is None else k1
+        self._check_count(array, k0, k1, out)
         self._ck(self._lib.epg_download(self._h, array, k0, k1, _dp(out)))
         return out
+
+    def _check_count(self, array, k0, k1, buf):
+        n = int(self._lib.epg_array_count(self._h, array, k0, k1))
+        if n >= 0 and buf.size != n:
+            raise ValueError("host buffer of %d doubles for device array %d, which holds %d" % (buf.size, array, n))
 
     def device_ptr(self, array):
         return self._lib.epg_device_ptr(self._h, array)
@@ -188,11 +199,25 @@ class Context:
         return torch.as_tensor(a, device=torch.device('cuda', self.device))
 
     def dsum_tensor(self):
-        """torch view (no copy) of EPG_DSUM = [sum dQi | sum dri | sum |delta_k|^2 | n_ok]."""
-        return self._alias(DSUM, self.d * self.d + self.d + 2)
+        """torch view (no copy) of EPG_DSUM = [sum dQi | sum dri | sum |delta_k|^2 | n_ok | slots]:
+        the buffer the ranks all-reduce once per EP iteration."""
+        return self._alias(DSUM, self.d * self.d + self.d + 2 + XCHG_SLOTS)
 
-    def delta_sums(self):
-        self._ck(self._lib.epg_delta_sums(self._h))
+    def delta_sums(self, with_norms=True, slots=None):
+        if slots is None:
+            slots = np.zeros(0)
+        slots = np.ascontiguousarray(slots, dtype=np.float64)
+        self._ck(self._lib.epg_delta_sums_ex(self._h, 1 if with_norms else 0, _dp(slots) if len(slots) else None,
+                                             len(slots)))
+
+    def read_exchange(self):
+        """(sum |delta_k|^2, n_ok, slots) of the (all-reduced) EPG_DSUM."""
+        d = self.d
+        buf = self.download(DSUM, np.empty(d * d + d + 2 + XCHG_SLOTS))
+        return float(buf[d * d + d]), int(round(buf[d * d + d + 1])), buf[d * d + d + 2:]
+
+    def update_from_sums(self, df):
+        self._ck(self._lib.epg_update_from_sums(self._h, float(df)))
 
     def delta_snr(self):
         """(|sum_k delta_k|^2, sum_k |delta_k|^2, n_ok) of the (all-reduced) EPG_DSUM."""

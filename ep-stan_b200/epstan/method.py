@@ -86,6 +86,9 @@ class Worker(object):
 
     DEFAULT_OPTIONS = {
         'init_prev'       : True,
+        # extension: with init_prev the built-in sampler also starts each warm-up from the metric and step
+        # size its previous run adapted (False: Stan's unit metric and step size 1 every EP iteration)
+        'adapt_prev'      : True,
         'prec_estim'      : 'sample',
         'prec_estim_skip' : 0,
         'verbose'         : False
@@ -158,6 +161,7 @@ class Worker(object):
             if self.stan_params['init'] not in ('random', '0', 0):
                 raise ValueError("built-in sampler supports init 'random' or '0' only")
         self.init_prev = options['init_prev']
+        self.adapt_prev = bool(options['adapt_prev'])
         self.init_orig = self.stan_params['init']
         if self.init_prev and not isinstance(self.init_orig, str):
             raise ValueError("Arg. `init` has to be a string if `init_prev` is True")
@@ -304,6 +308,7 @@ def _upload_site_block(shard, model, workers):
             if ji.min() < 0 or ji.max() >= J or np.any(np.diff(ji) < 0):
                 raise ValueError("`j_ind` must be sorted and within 1..J for every site")
     shard.ctx.upload_sites(model.model_id, D, k_lim, X, y, j_ind, Jk)
+    shard.ctx.set_option('carry_adapt', 1 if workers[0].adapt_prev else 0)
     shard.sites_uploaded = True
 
 
@@ -527,6 +532,9 @@ class Master(object):
 
         # shard + device context
         self.comm = self._comm_factory()
+        if K < self.comm.size:
+            raise ValueError("Fewer sites ({}) than ranks ({}): every rank needs at least one site"
+                             .format(K, self.comm.size))
         k_begin, k_end = self.comm.shard(K)
         ctx = self._context_factory(_pick_device(), _pick_stream(self.comm))
         ctx.init_state(k_end - k_begin, d)
@@ -619,7 +627,7 @@ class Master(object):
         if self.comm.size > 1:
             self._allreduce_device(self._shard.ctx.partial_tensor())
 
-    def _select_df(self, cap):
+    def _select_df(self, cap, exchanged=False):
         """Automatic damping (`df_select='snr'`; extension).
 
         At an EP fixed point every site delta has zero mean: the summed update is the sum of K
@@ -637,8 +645,9 @@ class Master(object):
         sites -- it enters the summed update K times and looks like signal.  At the floor 1/K the
         update is the average of the sites' tilted estimates and such a bias passes through once."""
         ctx = self._shard.ctx
-        ctx.delta_sums()
-        self._allreduce_device(ctx.dsum_tensor())
+        if not exchanged:                       # (several ranks: `_exchange` has reduced the sums already)
+            ctx.delta_sums()
+            self._allreduce_device(ctx.dsum_tensor())
         T2, S2, n_ok = ctx.delta_snr()
         d = self.dphi
         dof = d * (d + 1) / 2.0 + d
@@ -650,6 +659,83 @@ class Master(object):
         df = min(cap, max(self.df_min, raw)) if raw >= self.df_snr_min else min(cap, self.df_min)
         self.history['snr'].append((T2, N2, raw))
         return df
+
+    def _exchange(self, with_norms, n_fail, maxima):
+        """THE exchange of an EP iteration: one all-reduce(sum) of EPG_DSUM =
+        [sum_k dQi | sum_k dri | sum_k |delta_k|^2 | n_ok | slots].  The slots carry this rank's count of
+        failed sites and, in a per-rank block, its analytics maxima (summing blocks that are zero on every
+        other rank gathers them).  Returns (n_ok, n_fail, [max sampling time, max step size, max Rhat])."""
+        ctx, comm = self._shard.ctx, self.comm
+        slots = np.zeros(_lib.XCHG_SLOTS)
+        per = len(maxima) + 1
+        if 1 + per * comm.size > _lib.XCHG_SLOTS:
+            raise ValueError("too many ranks for the exchange slots")
+        slots[0] = n_fail
+        base = 1 + per * comm.rank              # this rank's block: [bit i set = value i present, values ...]
+        bits = 0
+        for i, v in enumerate(maxima):
+            if v is not None and np.isfinite(v):
+                bits |= 1 << i
+                slots[base + 1 + i] = v
+        slots[base] = float(bits)
+        ctx.delta_sums(with_norms=with_norms, slots=slots)
+        self._allreduce_device(ctx.dsum_tensor())
+        _, n_ok, red = ctx.read_exchange()
+        out = []
+        for i in range(len(maxima)):
+            vals = [red[1 + per * rk + 1 + i] for rk in range(comm.size)
+                    if (int(round(red[1 + per * rk])) >> i) & 1]
+            out.append(max(vals) if vals else -np.inf)
+        return n_ok, int(round(red[0])), out
+
+    def _update_without_exchange(self, df_first, verbose):
+        """Damped update after `_exchange` (several ranks).  Every rank forms the same proposal
+        Q_prev + df * sum_k dQi from the reduced sums and checks it and its OWN cavities, walking down the
+        damping ladder df, df*decay, ... without talking to the others.  Positive definiteness of the global
+        matrix and of every cavity is linear in df and holds at df = 0 (the current state), so a rank that
+        accepts df also accepts every smaller one: the consensus is the maximum of the local ladder
+        positions -- ONE scalar all-reduce per iteration however many retries there were
+        (reference method.py:1066-1146 broadcasts per attempt by construction: it is one process).
+        Returns (status, df, attempts): status 0 accepted, 1 invalid prior, 2 the ladder ran below
+        `df_treshold` somewhere (the caller falls back to the exchanging loop with its forcing branch)."""
+        ctx = self._shard.ctx
+        BIG = 1 << 30
+
+        def attempt(df):
+            ctx.update_partial(df)              # local Qi2 = Qi + df dQi (the cavities of the proposal need them)
+            ctx.update_from_sums(df)
+            if not ctx.update_finish():
+                return -1
+            return 1 if ctx.cavity(proposal=True)[1] else 0
+
+        j, df = 0, df_first
+        invalid = False
+        while True:
+            res = attempt(df)
+            if res == 1:
+                break
+            if res == -1 and self.iter == 1:
+                invalid = True                  # (the global matrix is the same on every rank: so is this flag)
+                break
+            df *= self.df_decay
+            j += 1
+            if verbose:
+                sys.stdout.write("\rNon pos. def. {}, reducing df to {:.3}".format(
+                    "posterior cov" if res == -1 else "cavity", df) + " " * 5 + "\b" * 5)
+                sys.stdout.flush()
+            if df < self.df_treshold:
+                j = BIG
+                break
+        if invalid:
+            return 1, df, j + 1
+        j_all = int(round(self.comm.allreduce_scalar(float(j), 'max')))
+        if j_all >= BIG:
+            return 2, df_first, 0
+        if j_all != j:
+            df = df_first * self.df_decay ** j_all
+            if attempt(df) != 1:
+                raise RuntimeError("damping consensus: a smaller damping factor failed where a larger one passed")
+        return 0, df, j_all + 1
 
     def _all_ranks(self, flag):
         if self.comm.size > 1:
@@ -806,23 +892,28 @@ class Master(object):
             oks = self._tilted_all(seeds[cur_iter], save_last_param)
             n_ok = int(oks.sum())
             n_fail = len(oks) - n_ok
-            if comm.size > 1:
+
+            def lmax(vals):
+                # (NaN = a site whose chains could not be initialised: it is a failed site, not a maximum)
+                vals = [v for v in vals if v is not None and np.isfinite(v)]
+                return max(vals) if vals else None
+            maxima = [lmax([w.last_time for w in local_workers]), lmax([w.last_msteps for w in local_workers]),
+                      lmax([w.last_mrhat for w in local_workers])]
+            exchanged = False
+            if comm.size > 1 and hasattr(ctx, 'update_from_sums'):
+                # one all-reduce carries the summed site deltas, the counts and the analytics maxima
+                n_ok, n_fail, maxima = self._exchange(self.df_select == 'snr', n_fail, maxima)
+                exchanged = True
+            elif comm.size > 1:
                 n_ok = int(round(comm.allreduce_scalar(n_ok, 'sum')))
                 n_fail = int(round(comm.allreduce_scalar(n_fail, 'sum')))
+                maxima = [comm.allreduce_scalar(-np.inf if v is None else v, 'max') for v in maxima]
             if verbose:
                 print("All sites ok" if n_fail == 0 else
                       ("Some sites failed and are not updated" if n_ok else "Every site failed"))
             if n_ok == 0:
                 return result(self.INFO_ALL_SITES_FAIL)
-
-            def gmax(vals):
-                # (NaN = a site whose chains could not be initialised: it is a failed site, not a maximum)
-                vals = [v for v in vals if v is not None and np.isfinite(v)]
-                v = max(vals) if vals else -np.inf
-                return comm.allreduce_scalar(v, 'max') if comm.size > 1 else v
-            stimes[cur_iter] = gmax([w.last_time for w in local_workers])
-            msteps[cur_iter] = gmax([w.last_msteps for w in local_workers])
-            mrhats[cur_iter] = gmax([w.last_mrhat for w in local_workers])
+            stimes[cur_iter], msteps[cur_iter], mrhats[cur_iter] = [-np.inf if v is None else v for v in maxima]
             # distribution of the per-site max split-Rhat behind that maximum (local shard)
             rh = np.array([w.last_mrhat for w in local_workers if w.last_mrhat is not None], dtype=np.float64)
             rh = rh[np.isfinite(rh)]
@@ -836,13 +927,26 @@ class Master(object):
             start_othertime = time.time()
             df = self.df0(self.iter)
             if self.df_select == 'snr':
-                df = self._select_df(df)
+                df = self._select_df(df, exchanged)
             df_first = df
             if verbose:
                 print("Iter {}, starting df {:.3g}".format(self.iter, df))
             failed_force_pos_def = False
             attempts = 0
-            while True:
+            fast = 2
+            if exchanged:
+                fast, df_acc, attempts_acc = self._update_without_exchange(df_first, verbose)
+                if fast == 1:
+                    if verbose:
+                        print("\nInvalid prior.")
+                    return result(self.INFO_INVALID_PRIOR)
+                if fast == 0:
+                    ctx.accept()
+                    self.history['df'].append(df_acc)
+                    self.history['attempts'].append(attempts_acc)
+                    self.history['n_ok'].append(n_ok)
+                    self.history['n_fail'].append(n_fail)
+            while fast == 2:
                 attempts += 1
                 # Qi2 = Qi + df dQi, Q = Q0 + sum_k Qi2 (method.py:1071-1074); the
                 # all-reduce is the only exchange between GPUs

@@ -34,6 +34,7 @@ extern "C" {
 typedef struct epg_ctx epg_ctx;
 
 #define EPG_VERSION 1
+#define EPG_XCHG_SLOTS 64      /* caller-defined doubles that ride on the per-iteration all-reduce */
 
 /* ---- device-resident arrays (ids for epg_upload / epg_download / epg_device_ptr) ---- */
 enum epg_array {
@@ -54,8 +55,9 @@ enum epg_array {
     EPG_PARTIAL = 14, /* [sum_k Qi2 | sum_k ri2 | n_ok] of this shard, d*d+d+1: the
                          NCCL all-reduce payload (method.py:1073-1074)     */
     EPG_TMEAN = 15, /* tilted means of the last moment matching  K*d (Worker.vec after tilted) */
-    EPG_DSUM = 16,  /* [sum_k dQi | sum_k dri | sum_k |delta_k|^2 | n_ok] of this shard, d*d+d+2
-                       (epg_delta_sums; all-reduced by the caller before epg_delta_snr)  */
+    EPG_DSUM = 16,  /* [sum_k dQi | sum_k dri | sum_k |delta_k|^2 | n_ok | EPG_XCHG_SLOTS caller slots] of this
+                       shard, d*d+d+2+EPG_XCHG_SLOTS doubles (epg_delta_sums[_ex]): THE buffer the ranks
+                       all-reduce (sum) once per EP iteration (method.py:1073-1074)  */
     EPG_NARRAYS = 17
 };
 
@@ -89,6 +91,8 @@ int epg_init_state(epg_ctx* ctx, int K, int d);
 int epg_upload(epg_ctx* ctx, int array, int k0, int k1, const double* host);
 int epg_download(epg_ctx* ctx, int array, int k0, int k1, double* host);
 void* epg_device_ptr(epg_ctx* ctx, int array);
+/* number of doubles epg_upload / epg_download move for this array and site range (k0,k1 ignored for global arrays) */
+int64_t epg_array_count(epg_ctx* ctx, int array, int k0, int k1);
 
 /* ---- cavity: Worker.cavity, method.py:267-302 (batched over sites) ----
  * proposal==0 uses (Qi,ri), 1 uses (Qi2,ri2).  Writes EPG_CAVQ / EPG_CAVM for
@@ -137,6 +141,19 @@ int epg_force_pd(epg_ctx* ctx, double thr, double min_eig, int32_t* forced_out, 
  *   independent zero-mean noise, i.e. about equal to the second. */
 int epg_delta_sums(epg_ctx* ctx);
 int epg_delta_snr(epg_ctx* ctx, double* stats_out);
+
+/* ---- one exchange per EP iteration (method.py:1073-1074 sums the sites on one host) ----
+ * epg_delta_sums_ex: epg_delta_sums with the Fisher norms optional (with_norms == 0: the sum_k |delta_k|^2
+ *   entry is 0) and `n_slots` <= EPG_XCHG_SLOTS caller-defined doubles appended (the rest zero) -- the host
+ *   puts its per-rank scalars there (failed-site counts, analytics maxima in per-rank slots), so that ONE
+ *   all-reduce(sum) of EPG_DSUM carries everything an iteration exchanges.  Also snapshots the current
+ *   global (Q, r).
+ * epg_update_from_sums: with EPG_DSUM all-reduced, sets EPG_PARTIAL so that the following
+ *   epg_update_finish yields the proposal Q = Q_prev + df * sum_k dQi, r = r_prev + df * sum_k dri --
+ *   identical on every rank, so damping retries need no further exchange of matrices
+ *   (epg_update_partial(df) still forms the local Qi2 = Qi + df dQi for the proposal cavities). */
+int epg_delta_sums_ex(epg_ctx* ctx, int with_norms, const double* slots, int n_slots);
+int epg_update_from_sums(epg_ctx* ctx, double df);
 
 /* ---- damping sweep: experiment/find_damp.py:144-174 + kl_mvn :32-51 ----
  * For each dfs[i]: rebuild the global approximation from (Qi,ri,dQi,dri),
@@ -197,13 +214,18 @@ int epg_tilted_sample(epg_ctx* ctx, int k0, int k1, const uint32_t* seeds,
                       const epg_sampler_opts* opts, double* msteps_out, double* mrhat_out,
                       int64_t* n_leapfrog_out, double* seconds);
 
-/* Marks local sites whose chains the next epg_tilted_sample with init_mode 2 starts from Stan's random
- * initialisation U(-2,2) instead of their previous last draws (an extension: with init_prev,
- * method.py:404-406, a chain that got stuck -- e.g. in a funnel neck with a collapsed step size -- would
- * otherwise stay stuck for the rest of the EP run).  The marks are consumed by that call. */
+/* Marks local sites whose chains the next epg_tilted_sample with init_mode 2 starts afresh -- phi within one
+ * conditional cavity standard deviation of the cavity mean, the site-local latents in U(-1,1) -- instead of
+ * from their previous last draws (an extension: with init_prev, method.py:404-406, a chain that got stuck,
+ * e.g. far out with a collapsed step size, would otherwise stay stuck for the rest of the EP run; Stan's
+ * U(-2,2) is no remedy late in a run, when the cavity is thousands of times narrower than that).
+ * The marks are consumed by that call. */
 int epg_reinit_sites(epg_ctx* ctx, int n, const int32_t* sites);
 
-/* Options.  "use_tc" (default 1): use the tcgen05/TMA likelihood pass when the
+/* Options.  "carry_adapt" (default 1): a run with init_mode 2 (init_prev) starts its warm-up from the metric
+ * and step size the previous run of the same chain ended with, instead of Stan's unit metric and step size 1
+ * (an extension in the spirit of init_prev, method.py:404-406; the warm-up itself -- dual averaging, variance
+ * windows -- still runs in full); 0 = Stan's defaults.  "use_tc" (default 1): use the tcgen05/TMA likelihood pass when the
  * shapes allow it (single-group sites, D+1 <= 64, chains <= 16); 0 forces the
  * fp32 SIMT pass.  "pingpong" (default 0): 1 = with the tensor-core pass, more
  * sites than SMs and design matrices that stay L2-resident, run the persistent

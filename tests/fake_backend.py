@@ -9,6 +9,7 @@ import torch
 from oracle import ep_linalg as orc
 
 (Q, R, Q0, R0, QI, RI, QI2, RI2, DQI, DRI, CAVQ, CAVM, S, M, PARTIAL, TMEAN, DSUM) = range(17)
+XCHG_SLOTS = 64
 _SITE3 = (QI, QI2, DQI, CAVQ)
 _SITE2 = (RI, RI2, DRI, CAVM, TMEAN)
 
@@ -32,7 +33,8 @@ class OracleContext(object):
             self.a[i] = np.zeros(d)
         self.a[PARTIAL] = np.zeros(d * d + d + 1)
         self._partial_t = torch.from_numpy(self.a[PARTIAL])
-        self.a[DSUM] = np.zeros(d * d + d + 2)
+        self.a[DSUM] = np.zeros(d * d + d + 2 + XCHG_SLOTS)
+        self._qprev = None
         self._dsum_t = torch.from_numpy(self.a[DSUM])
         self._ok = np.ones(K, dtype=bool)
         self.draws = None
@@ -65,10 +67,14 @@ class OracleContext(object):
     def dsum_tensor(self):
         return self._dsum_t
 
-    def delta_sums(self):
+    def delta_sums(self, with_norms=True, slots=None):
         d = self.d
         S2 = sum(orc.fisher_norm2(self.a[Q], self.a[R], self.a[DQI][:, :, k], self.a[DRI][:, k])
-                 for k in range(self.K) if self._ok[k])
+                 for k in range(self.K) if self._ok[k]) if with_norms else 0.0
+        self._qprev = (self.a[Q].copy(), self.a[R].copy())
+        self.a[DSUM][d * d + d + 2:] = 0.0
+        if slots is not None:
+            self.a[DSUM][d * d + d + 2:d * d + d + 2 + len(slots)] = slots
         self.a[DSUM][:d * d] = self.a[DQI].sum(axis=2).ravel(order='F')
         self.a[DSUM][d * d:d * d + d] = self.a[DRI].sum(axis=1)
         self.a[DSUM][d * d + d] = S2
@@ -79,6 +85,17 @@ class OracleContext(object):
         T2 = orc.fisher_norm2(self.a[Q], self.a[R], self.a[DSUM][:d * d].reshape(d, d, order='F'),
                               self.a[DSUM][d * d:d * d + d])
         return T2, float(self.a[DSUM][d * d + d]), int(round(self.a[DSUM][d * d + d + 1]))
+
+    def read_exchange(self):
+        d = self.d
+        b = self.a[DSUM]
+        return float(b[d * d + d]), int(round(b[d * d + d + 1])), b[d * d + d + 2:].copy()
+
+    def update_from_sums(self, df):
+        d = self.d
+        Qp, rp = self._qprev
+        self.a[PARTIAL][:d * d] = ((Qp - self.a[Q0]) + df * self.a[DSUM][:d * d].reshape(d, d, order='F')).ravel(order='F')
+        self.a[PARTIAL][d * d:d * d + d] = (rp - self.a[R0]) + df * self.a[DSUM][d * d:d * d + d]
 
     def on_torch_stream(self):
         return True
@@ -164,6 +181,9 @@ class OracleContext(object):
                 self.a[QI][np.arange(self.d), np.arange(self.d), k] += min_eig - lam[k]
                 forced[k] = True
         return forced, lam
+
+    def set_option(self, name, value):
+        pass
 
     def close(self):
         pass

@@ -157,7 +157,7 @@ def test_delta_snr_statistic(K, d):
     oT2 = orc.fisher_norm2(Q, r, dQ.sum(axis=2), dr.sum(axis=1))
     assert n_ok == K
     assert abs(S2 - oS2) <= 1e-10 * oS2 and abs(T2 - oT2) <= 1e-10 * oT2
-    ds = ctx.download(_lib.DSUM, np.empty(d * d + d + 2))
+    ds = ctx.download(_lib.DSUM, np.empty(d * d + d + 2 + _lib.XCHG_SLOTS))
     assert relerr(ds[:d * d].reshape(d, d, order='F'), dQ.sum(axis=2)) < 1e-13
     assert relerr(ds[d * d:d * d + d], dr.sum(axis=1)) < 1e-13
 

@@ -198,8 +198,8 @@ def test_init_prev_and_zero_init():
 
 
 def test_reinit_sites_overrides_init_prev():
-    """epg_reinit_sites: a marked site's chains start from U(-2,2) in the next init_prev run (as in a run with
-    init 'random' and the same seed); the other sites continue from their last draws; the mark is consumed."""
+    """epg_reinit_sites: a marked site's chains start afresh (around the cavity mean) in the next init_prev run;
+    the other sites continue from their last draws; the mark is consumed."""
     sites = [synth.make_site('m1b', 200, 3, 1, seed=5 + k) for k in range(3)]
     n = 4 * 30
 
@@ -217,9 +217,10 @@ def test_reinit_sites_overrides_init_prev():
 
     b0, c0 = run(None)
     b1, c1 = run(1)
-    br, _ = run(None, second_mode=0)
     assert np.array_equal(b0[0], b1[0]) and np.array_equal(b0[2], b1[2])       # unmarked sites: unchanged
-    assert not np.array_equal(b0[1], b1[1]) and np.array_equal(b1[1], br[1])   # marked site: the random-init run
+    assert not np.array_equal(b0[1], b1[1])                                    # marked site: a fresh start
+    # ... from which the sampler reaches the same distribution
+    assert np.all(np.abs(b0[1].mean(axis=1) - b1[1].mean(axis=1)) < 5 * b0[1].std(axis=1) / np.sqrt(n / 10))
     assert np.array_equal(c0[0], c1[0]) and not np.array_equal(c0[1], c1[1])   # third run: init_prev everywhere again
     assert np.all(np.isfinite(b1)) and np.all(np.isfinite(c1))
 
