@@ -39,6 +39,7 @@ struct CvArgs {
     double* G1;              // [batch][nf*nf]
     double* G2;              // [batch][nf*nf]
     double* res;             // [batch][d2] stage result
+    double* aout;            // coefficients a of the stage (ret_a): [batch][nf*nf] (multiple_cv) or [batch][nf]; may be null
     int multiple_cv;
     double regulate_a, max_a, m_treshold;
 };
@@ -352,16 +353,21 @@ __global__ void __launch_bounds__(1024) k_cv_solve(const CvArgs a, int stage) {
         }
     }
     __syncthreads();
+    // regulate / clip a (util.py:227-230), keep a copy for ret_a
+    double* aout = a.aout ? a.aout + (size_t)b * nf * nf : nullptr;
+    for (size_t e = tid; e < (size_t)nf * nf; e += nt) {
+        double aij = B[e];
+        if (a.regulate_a > 0.0) aij *= a.regulate_a;
+        if (a.max_a > 0.0) aij = fmin(fmax(aij, -a.max_a), a.max_a);
+        B[e] = aij;
+        if (aout) aout[e] = aij;
+    }
+    __syncthreads();
     const double* hm = a.hm + (size_t)b * a.d2;
     const double* fm = a.fm + (size_t)b * a.d2;
     for (int j = tid; j < nf; j += nt) {
         double s = 0.0;
-        for (int i = 0; i < nf; ++i) {
-            double aij = B[(size_t)i * nf + j];
-            if (a.regulate_a > 0.0) aij *= a.regulate_a;
-            if (a.max_a > 0.0) aij = fmin(fmax(aij, -a.max_a), a.max_a);
-            s += hm[i] * aij;
-        }
+        for (int i = 0; i < nf; ++i) s += hm[i] * B[(size_t)i * nf + j];
         a.res[(size_t)b * a.d2 + j] = fm[j] - s;
     }
 }
@@ -411,6 +417,7 @@ __global__ void k_cv_diag(const CvArgs a, int stage) {
         if (a.regulate_a > 0.0) av *= a.regulate_a;
         if (a.max_a > 0.0) av = fmin(fmax(av, -a.max_a), a.max_a);
         a.res[(size_t)b * a.d2 + e] = fme - a.hm[(size_t)b * a.d2 + e] * av;
+        if (a.aout) a.aout[(size_t)b * nf + e] = av;
     }
 }
 
@@ -435,6 +442,14 @@ __global__ void k_cv_store(const CvArgs a, int stage) {
 extern "C" int epg_cv_moments(epg_ctx* c, int batch, int n, int d, const double* draws, const double* lp,
                               const double* Q_tilde, const double* r_tilde, int multiple_cv, double regulate_a,
                               double max_a, double m_treshold, double* S_hat, double* m_hat, int32_t* used_cv) {
+    return epg_cv_moments_ex(c, batch, n, d, draws, lp, Q_tilde, r_tilde, multiple_cv, regulate_a, max_a, m_treshold,
+                             S_hat, m_hat, used_cv, nullptr, nullptr);
+}
+
+extern "C" int epg_cv_moments_ex(epg_ctx* c, int batch, int n, int d, const double* draws, const double* lp,
+                                 const double* Q_tilde, const double* r_tilde, int multiple_cv, double regulate_a,
+                                 double max_a, double m_treshold, double* S_hat, double* m_hat, int32_t* used_cv,
+                                 double* a_S_out, double* a_m_out) {
     if (batch < 1 || n < 2 || d < 1 || d > 200 || !draws || !lp || !Q_tilde || !r_tilde || !S_hat || !m_hat)
         return epg_fail_msg(c, "epg_cv_moments: bad args");
     const int d2 = d * (d + 1) / 2;
@@ -453,6 +468,8 @@ extern "C" int epg_cv_moments(epg_ctx* c, int batch, int n, int d, const double*
                  o_fm = take((size_t)batch * d2), o_hm = take((size_t)batch * d2), o_res = take((size_t)batch * d2),
                  o_G1 = take((size_t)chunk * per_item_gram / 2 + 2), o_G2 = take((size_t)chunk * per_item_gram / 2 + 2),
                  o_feat = take((size_t)d2 + 2), o_status = take((size_t)batch / 2 + 2);
+    const size_t a_m_cnt = (size_t)batch * (multiple_cv ? dd : (size_t)d), a_S_cnt = (size_t)batch * (multiple_cv ? (size_t)d2 * d2 : (size_t)d2);
+    const size_t o_am = take(a_m_out ? a_m_cnt : 0), o_aS = take(a_S_out ? a_S_cnt : 0);
     EPG_CHECK(c, epg_reserve((void**)&c->util_buf, &c->util_bytes, sizeof(double) * off));
     double* base = c->util_buf;
     CvArgs a;
@@ -463,6 +480,10 @@ extern "C" int epg_cv_moments(epg_ctx* c, int batch, int n, int d, const double*
     a.feat = reinterpret_cast<const int2*>(base + o_feat);
     a.status = reinterpret_cast<int*>(base + o_status);
     a.multiple_cv = multiple_cv; a.regulate_a = regulate_a; a.max_a = max_a; a.m_treshold = m_treshold;
+    a.aout = nullptr;
+    // (items that take the plain-estimate fallback report zero coefficients: util.py:364-365)
+    if (a_m_out) EPG_CHECK(c, cudaMemsetAsync(base + o_am, 0, sizeof(double) * a_m_cnt, c->stream));
+    if (a_S_out) EPG_CHECK(c, cudaMemsetAsync(base + o_aS, 0, sizeof(double) * a_S_cnt, c->stream));
     std::vector<int2> feat(d2);
     {
         int e = 0;
@@ -484,6 +505,7 @@ extern "C" int epg_cv_moments(epg_ctx* c, int batch, int n, int d, const double*
     const size_t sm_gram = sizeof(double) * ((size_t)d * CV_T + CV_T + 2 * (size_t)d + 3 * CV_T * CV_TILE);
     for (int stage = 0; stage < 2; ++stage) {
         const int nf = stage == 0 ? d : d2;
+        a.aout = stage == 0 ? (a_m_out ? base + o_am : nullptr) : (a_S_out ? base + o_aS : nullptr);
         k_cv_sums<<<dim3((nf + 127) / 128, batch), 128, sm_sums, st>>>(a, stage);
         c->launches++;
         if (multiple_cv) {
@@ -506,6 +528,8 @@ extern "C" int epg_cv_moments(epg_ctx* c, int batch, int n, int d, const double*
     }
     EPG_CHECK(c, cudaMemcpyAsync(S_hat, base + o_sh, sizeof(double) * batch * dd, cudaMemcpyDeviceToHost, st));
     EPG_CHECK(c, cudaMemcpyAsync(m_hat, base + o_mh, sizeof(double) * (size_t)batch * d, cudaMemcpyDeviceToHost, st));
+    if (a_m_out) EPG_CHECK(c, cudaMemcpyAsync(a_m_out, base + o_am, sizeof(double) * a_m_cnt, cudaMemcpyDeviceToHost, st));
+    if (a_S_out) EPG_CHECK(c, cudaMemcpyAsync(a_S_out, base + o_aS, sizeof(double) * a_S_cnt, cudaMemcpyDeviceToHost, st));
     std::vector<int> stat(batch);
     EPG_CHECK(c, cudaMemcpyAsync(stat.data(), a.status, sizeof(int) * batch, cudaMemcpyDeviceToHost, st));
     EPG_CHECK(c, cudaStreamSynchronize(st));

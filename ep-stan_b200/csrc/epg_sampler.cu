@@ -192,6 +192,7 @@ enum { PH_START = 0, PH_START_WAIT, PH_SS_WAIT, PH_TREE_WAIT, PH_DONE, PH_DEAD }
 
 struct ChainS {
     int phase, iter, depth, nleaf, sign, n_leap_tr, ss_dir, ss_first, init_tries, restart_ss;
+    int carried;                  // the warm-up started from the previous run's adapted metric / step size
     int init_mode;                // SamplerArgs::init_mode, or 3 (around the cavity mean) for a site marked by epg_reinit_sites
     uint32_t rng;
     float eps;
@@ -937,6 +938,10 @@ __device__ void end_transition(const CX& x, ChainS& s, int c_local, int k_global
             float* minv = x.v(V_MINV); float* wm = x.v(V_WMEAN); float* w2 = x.v(V_WM2);
             for (int i = x.lane; i < x.p; i += 32) {
                 const float var = w2[i] / (n - 1.0f);
+                // (Stan's regularisation towards the absolute scale 1e-3 is kept also when the metric is carried over
+                //  between EP iterations: shrinking towards the carried value instead was measured -- shorter
+                //  trees, 3.8 s instead of 5.8 s per config-4 iteration, but underestimated variances then feed
+                //  back into the next run: median split-Rhat 1.02 -> 1.06 and the EP iteration became unstable)
                 minv[i] = (n / (n + 5.0f)) * var + 1e-3f * (5.0f / (n + 5.0f));
                 wm[i] = 0.0f; w2[i] = 0.0f;
             }
@@ -1195,14 +1200,16 @@ __device__ __forceinline__ void init_chains(const SamplerArgs& a, const SiteView
         // 90 % of every warm-up crawl at the scale of the tightest cavity direction with saturated trees.
         // A re-initialised site (mode 3) starts from the conditional cavity variances instead.
         float eps0 = 1.0f;
+        bool carried = false;
         if (im == 2 && a.carry_adapt) {
             const float e = a.last_eps[cg];
-            if (e > 0.0f && isfinite(e)) eps0 = e;
+            if (e > 0.0f && isfinite(e)) { eps0 = e; carried = true; }     // (written together with last_minv)
         }
         if (lane == 0) {
             memset(&s, 0, sizeof(ChainS));
             s.phase = PH_START;
             s.init_mode = im;
+            s.carried = carried ? 1 : 0;
             s.eps = eps0;
             s.mu = log(10.0 * (double)eps0);
             s.rng = 0;
@@ -1212,7 +1219,7 @@ __device__ __forceinline__ void init_chains(const SamplerArgs& a, const SiteView
         const int vecs[] = {V_WMEAN, V_WM2, V_RS0, V_RQ0, V_RS1, V_RQ1};
         for (int i = lane; i < a.P; i += 32) {
             float mv = 1.0f;
-            if (im == 2 && a.carry_adapt) {
+            if (carried) {
                 const float v = a.last_minv[(size_t)cg * a.P + i];
                 if (v > 0.0f && isfinite(v)) mv = v;
             } else if (im == 3 && i < a.d) {

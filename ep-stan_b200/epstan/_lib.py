@@ -73,6 +73,9 @@ SYMBOLS = [
     ('epg_cv_moments', C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, _c_double_p, _c_double_p, _c_double_p,
                                  _c_double_p, C.c_int, C.c_double, C.c_double, C.c_double, _c_double_p,
                                  _c_double_p, _c_int32_p]),
+    ('epg_cv_moments_ex', C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, _c_double_p, _c_double_p, _c_double_p,
+                                 _c_double_p, C.c_int, C.c_double, C.c_double, C.c_double, _c_double_p,
+                                 _c_double_p, _c_int32_p, _c_double_p, _c_double_p]),
     ('epg_upload_sites', C.c_int, [C.c_void_p, C.c_int, C.c_int, _c_int64_p, _c_double_p, _c_int64_p,
                                    _c_int32_p, _c_int32_p]),
     ('epg_tilted_sample', C.c_int, [C.c_void_p, C.c_int, C.c_int, _c_uint32_p, C.POINTER(SamplerOpts),
@@ -328,8 +331,9 @@ class Context:
         return out, ok.astype(bool)
 
     def cv_moments(self, draws, lp, Q_tilde, r_tilde, multiple_cv=True, regulate_a=None, max_a=None,
-                   m_treshold=0.9):
-        """draws: (batch, d, n); lp: (batch, n); Q_tilde: (batch,d,d); r_tilde: (batch,d)."""
+                   m_treshold=0.9, ret_a=False):
+        """draws: (batch, d, n); lp: (batch, n); Q_tilde: (batch,d,d); r_tilde: (batch,d).
+        ret_a: also return the coefficient arrays (a_S, a_m) of every item."""
         draws = _f64(draws, 'C')
         batch, d, n = draws.shape
         lp = _f64(lp, 'C')
@@ -338,10 +342,18 @@ class Context:
         S_hat = np.empty((batch, d, d))
         m_hat = np.empty((batch, d))
         used = np.empty(batch, dtype=np.int32)
-        self._ck(self._lib.epg_cv_moments(
+        d2 = d * (d + 1) // 2
+        a_S = a_m = None
+        if ret_a:
+            a_S = np.empty((batch, d2, d2) if multiple_cv else (batch, d2))
+            a_m = np.empty((batch, d, d) if multiple_cv else (batch, d))
+        self._ck(self._lib.epg_cv_moments_ex(
             self._h, batch, n, d, _dp(draws), _dp(lp), _dp(Qt), _dp(rt), int(bool(multiple_cv)),
             float(regulate_a or 0.0), float(max_a or 0.0), float(m_treshold or 0.0),
-            _dp(S_hat), _dp(m_hat), used.ctypes.data_as(_c_int32_p)))
+            _dp(S_hat), _dp(m_hat), used.ctypes.data_as(_c_int32_p),
+            _dp(a_S) if ret_a else None, _dp(a_m) if ret_a else None))
+        if ret_a:
+            return S_hat, m_hat, used, a_S, a_m
         return S_hat, m_hat, used
 
     # ---- sampler ----

@@ -105,21 +105,20 @@ def cv_moments(samp, lp, Q_tilde, r_tilde, S_tilde=None, m_tilde=None,
     """Approximate moments using a Gaussian control variate (reference
     util.py:245-411).  ``lp`` must be normalised.  ``S_tilde``, ``m_tilde`` and
     ``ldet_Q_tilde`` are accepted for signature compatibility and recomputed on
-    the device from ``(Q_tilde, r_tilde)``.  ``ret_a`` is not supported (the
-    coefficient matrices never leave the GPU).
+    the device from ``(Q_tilde, r_tilde)``.
 
-    Returns ``(S_hat, m_hat, treshold_exceeded)``.
+    Returns ``(S_hat, m_hat, treshold_exceeded)`` and, with ``ret_a``, the
+    coefficient arrays ``a_S, a_m`` (0, 0 when the plain estimates were returned).
     """
-    if ret_a:
-        raise NotImplementedError("ret_a=True is not supported by the GPU implementation")
     samp = np.asarray(samp, dtype=np.float64)
     if samp.ndim == 1:
         samp = samp[:, None]
     n, d = samp.shape
-    S, m, used = default_context().cv_moments(
+    res = default_context().cv_moments(
         np.ascontiguousarray(samp.T)[None], np.asarray(lp, dtype=np.float64)[None],
         np.asarray(Q_tilde, dtype=np.float64)[None], np.asarray(r_tilde, dtype=np.float64)[None],
-        multiple_cv=multiple_cv, regulate_a=regulate_a, max_a=max_a, m_treshold=m_treshold)
+        multiple_cv=multiple_cv, regulate_a=regulate_a, max_a=max_a, m_treshold=m_treshold, ret_a=ret_a)
+    S, m, used = res[:3]
     if used[0] < 0:
         raise LinAlgError("control variate system is singular or Q_tilde not positive definite")
     if S_hat is None:
@@ -128,6 +127,10 @@ def cv_moments(samp, lp, Q_tilde, r_tilde, S_tilde=None, m_tilde=None,
         m_hat = np.empty(d)
     np.copyto(S_hat, S[0])
     np.copyto(m_hat, m[0])
+    if ret_a:
+        if not used[0]:
+            return S_hat, m_hat, False, 0, 0
+        return S_hat, m_hat, True, res[3][0], res[4][0]
     return S_hat, m_hat, bool(used[0])
 
 

@@ -181,6 +181,13 @@ int epg_cv_moments(epg_ctx* ctx, int batch, int n, int d, const double* draws, c
                    const double* Q_tilde, const double* r_tilde, int multiple_cv,
                    double regulate_a, double max_a, double m_treshold,
                    double* S_hat, double* m_hat, int32_t* used_cv);
+/* the same, additionally returning the control-variate coefficients (cv_moments(..., ret_a=True), util.py:396-410):
+ *   a_m_out [batch][d*d] and a_S_out [batch][d2*d2] (row-major, first index = control feature) with multiple_cv,
+ *   [batch][d] and [batch][d2] without; zeros for items that took the plain fallback; either may be NULL. */
+int epg_cv_moments_ex(epg_ctx* ctx, int batch, int n, int d, const double* draws, const double* lp,
+                      const double* Q_tilde, const double* r_tilde, int multiple_cv,
+                      double regulate_a, double max_a, double m_treshold,
+                      double* S_hat, double* m_hat, int32_t* used_cv, double* a_S_out, double* a_m_out);
 
 /* ---- site data + tilted sampling: Worker.tilted first half, method.py:338-408,
  *      _sample_stan :43-118, stan_sample_time util.py:692-724 (PyStan NUTS) ----

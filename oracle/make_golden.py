@@ -201,6 +201,8 @@ def gen_cv(ep, out):
             t = '%s_%s' % (tag, 'multi' if mcv else 'single')
             out['cv_%s_S' % t], out['cv_%s_m' % t] = S_hat, m_hat
             out['cv_%s_used' % t] = np.array(used)
+            _, _, _, a_S, a_m = u.cv_moments(samp.copy(), lp, Q2, r2, multiple_cv=mcv, ret_a=True)
+            out['cv_%s_aS' % t], out['cv_%s_am' % t] = np.array(a_S), np.array(a_m)
         # treshold fallback: control variate far from the sample
         m3 = m1 + 5.0
         Q3, r3 = u.invert_normal_params(S2, m3)

@@ -301,9 +301,8 @@ def test_cv_moments_vs_reference(ep, golden, tag, seed, n, d):
     g = golden['cv']
     c = gi.cv_case(seed, n, d)
     Q2, r2 = orc.invert_normal_params(c['S2'], c['m2'])
-    # the d2 x d2 Gram system is ill-conditioned: LU-vs-LU agreement is limited by
-    # cond * eps (the pinned oracle itself only reaches 1e-7 against the reference here)
-    tol = 1e-9 if d <= 4 else 1e-6
+    # north_star check (a): 1e-10 relative in fp64 (the d2 x d2 Gram system has cond ~4e4 at d = 20)
+    tol = 1e-10
     for mcv in (True, False):
         t = '%s_%s' % (tag, 'multi' if mcv else 'single')
         S, m, used = ep.util.cv_moments(c['samp'].copy(), c['lp'], Q2, r2, multiple_cv=mcv)
@@ -311,8 +310,15 @@ def test_cv_moments_vs_reference(ep, golden, tag, seed, n, d):
         assert relerr(m, g['cv_%s_m' % t]) < tol
         assert relerr(S, g['cv_%s_S' % t]) < tol
         assert np.array_equal(S, S.T)
+        # ret_a=True: the coefficient arrays of the reference (same shapes; the linear solve behind them has a
+        # condition number of ~4e4 at d = 20, hence 1e-8 on the coefficients themselves)
+        S2_, m2_, used2, a_S, a_m = ep.util.cv_moments(c['samp'].copy(), c['lp'], Q2, r2, multiple_cv=mcv, ret_a=True)
+        assert used2 == used and np.array_equal(S2_, S) and np.array_equal(m2_, m)
+        assert a_S.shape == g['cv_%s_aS' % t].shape and relerr(a_S, g['cv_%s_aS' % t]) < 1e-8
+        assert a_m.shape == g['cv_%s_am' % t].shape and relerr(a_m, g['cv_%s_am' % t]) < 1e-8
     Q3, r3 = orc.invert_normal_params(c['S2'], c['m3'])
     S, m, used = ep.util.cv_moments(c['samp'].copy(), c['lp'], Q3, r3)
+    assert ep.util.cv_moments(c['samp'].copy(), c['lp'], Q3, r3, ret_a=True)[3:] == (0, 0)
     assert used is False
     assert relerr(m, g['cv_%s_fallback_m' % tag]) < TOL
     assert relerr(S, g['cv_%s_fallback_S' % tag]) < TOL
@@ -340,5 +346,5 @@ def test_cv_moments_batched_config2(ep):
         for k in (0, 17, 63):
             oS, om, oused = orc.cv_moments(*cases[k], multiple_cv=mcv, regulate_a=0.9, max_a=5.0)
             assert bool(used[k]) == oused
-            assert relerr(m[k], om) < 1e-6 and relerr(S[k], oS) < 1e-6
+            assert relerr(m[k], om) < 1e-10 and relerr(S[k], oS) < 1e-10
     ctx.close()
