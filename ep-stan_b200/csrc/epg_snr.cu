@@ -185,6 +185,42 @@ SnrPlan snr_plan(int K, int d) {
     return p;
 }
 
+// per site: mean of the draws, centred scatter and the outer product of the mean:
+// out[k] = [m_k (d) | sum_t (x_t - m_k)(x_t - m_k)' (d*d) | m_k m_k' (d*d)]   (Master.mix_phi, method.py:1280-1298)
+__global__ void k_site_scatter(const double* __restrict__ draws, int n, int d, double* __restrict__ out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* mean = reinterpret_cast<double*>(smem_raw);
+    const int k = blockIdx.x;
+    const double* x = draws + (size_t)k * d * n;
+    double* o = out + (size_t)k * (d + 2 * (size_t)d * d);
+    for (int i = threadIdx.x; i < d; i += blockDim.x) {
+        double s = 0.0;
+        for (int t = 0; t < n; ++t) s += x[(size_t)i * n + t];
+        mean[i] = s / n;
+        o[i] = mean[i];
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < d * d; e += blockDim.x) {
+        const int j = e / d, i = e - j * d;
+        if (j > i) continue;                                  // lower triangle, mirrored
+        const double mi = mean[i], mj = mean[j];
+        const double* xi = x + (size_t)i * n;
+        const double* xj = x + (size_t)j * n;
+        double a0 = 0.0, a1 = 0.0;
+        int t = 0;
+        for (; t + 2 <= n; t += 2) {
+            a0 = fma(xi[t] - mi, xj[t] - mj, a0);
+            a1 = fma(xi[t + 1] - mi, xj[t + 1] - mj, a1);
+        }
+        if (t < n) a0 = fma(xi[t] - mi, xj[t] - mj, a0);
+        const double acc = a0 + a1;
+        o[d + i + (size_t)j * d] = acc;
+        o[d + j + (size_t)i * d] = acc;
+        o[d + (size_t)d * d + i + (size_t)j * d] = mi * mj;
+        o[d + (size_t)d * d + j + (size_t)i * d] = mi * mj;
+    }
+}
+
 int launch_norms(epg_ctx* c, const SnrPlan& p, const double* dQ, const double* dr, double* out, int batch) {
     const int d = c->d;
     double* buf = c->snr_buf;
@@ -278,6 +314,28 @@ __global__ void k_partial_from_sums(const double* __restrict__ qprev, const doub
     if (e >= dd + d) return;
     const double base = e < dd ? qprev[e] - Q0[e] : qprev[e] - r0[e - dd];
     partial[e] = base + df * dsum[e];
+}
+
+// Sums over the local sites of [m_k | scatter_k | m_k m_k'] of the phi draws in the device draw buffer
+// (d + 2 d*d doubles): what Master.mix_phi pools (method.py:1250-1301); additive over ranks.
+int epg_mix_phi_sums(epg_ctx* c, int n, double* sums_out) {
+    if (!c->draws || n != c->draws_n || n < 2 || !sums_out) return epg_fail_msg(c, "epg_mix_phi_sums: no resident draws for this n");
+    const int d = c->d, K = c->K;
+    const size_t E = (size_t)d + 2 * (size_t)d * d;
+    const SnrPlan p = snr_plan(K, d);
+    const size_t need = sizeof(double) * (E * K + (size_t)p.nchunks * E + E);
+    EPG_CHECK(c, epg_reserve((void**)&c->util_buf, &c->util_bytes, need));
+    double* per = c->util_buf, *part = per + E * K, *tot = part + (size_t)p.nchunks * E;
+    k_site_scatter<<<K, 256, sizeof(double) * d, c->stream>>>(c->draws, n, d, per);
+    SNR_LAUNCH_CHECK(c);
+    dim3 grid((unsigned)((E + 255) / 256), p.nchunks);
+    k_site_sum_partial2<<<grid, 256, 0, c->stream>>>(per, part, K, (int)E, p.ks);
+    SNR_LAUNCH_CHECK(c);
+    k_sum_chunks2<<<(unsigned)((E + 255) / 256), 256, 0, c->stream>>>(part, tot, (int)E, p.nchunks);
+    SNR_LAUNCH_CHECK(c);
+    EPG_CHECK(c, cudaMemcpyAsync(sums_out, tot, sizeof(double) * E, cudaMemcpyDeviceToHost, c->stream));
+    EPG_CHECK(c, cudaStreamSynchronize(c->stream));
+    return 0;
 }
 
 int epg_update_from_sums(epg_ctx* c, double df) {

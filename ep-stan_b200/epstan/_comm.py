@@ -29,6 +29,9 @@ class Comm(object):
     def allgather_sites(self, local, K, axis):
         return local
 
+    def allreduce_array(self, arr):
+        return arr
+
     def barrier(self):
         pass
 
@@ -66,6 +69,13 @@ class TorchComm(Comm):
         t = torch.tensor([float(value)], dtype=torch.float64, device=self._device())
         self._dist.all_reduce(t, op=ops[op], group=self.group)
         return float(t.item())
+
+    def allreduce_array(self, arr):
+        """Sum of a small host array over the ranks."""
+        import torch
+        t = torch.from_numpy(np.ascontiguousarray(arr, dtype=np.float64)).to(self._device())
+        self._dist.all_reduce(t, op=self._dist.ReduceOp.SUM, group=self.group)
+        return t.cpu().numpy()
 
     def allgather_sites(self, local, K, axis):
         """Concatenate per-rank site blocks (split along `axis`) into the full array."""

@@ -64,6 +64,7 @@ SYMBOLS = [
     ('epg_delta_snr', C.c_int, [C.c_void_p, _c_double_p]),
     ('epg_delta_sums_ex', C.c_int, [C.c_void_p, C.c_int, _c_double_p, C.c_int]),
     ('epg_update_from_sums', C.c_int, [C.c_void_p, C.c_double]),
+    ('epg_mix_phi_sums', C.c_int, [C.c_void_p, C.c_int, _c_double_p]),
     ('epg_damp_sweep', C.c_int, [C.c_void_p, C.c_int, _c_double_p, _c_double_p, _c_double_p,
                                  _c_double_p, _c_double_p]),
     ('epg_invert_normal_params', C.c_int, [C.c_void_p, C.c_int, C.c_int, _c_double_p, _c_double_p, C.c_int,
@@ -218,6 +219,11 @@ class Context:
         d = self.d
         buf = self.download(DSUM, np.empty(d * d + d + 2 + XCHG_SLOTS))
         return float(buf[d * d + d]), int(round(buf[d * d + d + 1])), buf[d * d + d + 2:]
+
+    def mix_phi_sums(self, n):
+        out = np.empty(self.d + 2 * self.d * self.d)
+        self._ck(self._lib.epg_mix_phi_sums(self._h, int(n), _dp(out)))
+        return out
 
     def update_from_sums(self, df):
         self._ck(self._lib.epg_update_from_sums(self._h, float(df)))

@@ -1006,9 +1006,32 @@ class Master(object):
         return res
 
     def mix_phi(self, out_S=None, out_m=None):
-        raise NotImplementedError(
-            "mix_phi is outside the EP inner loop (SURVEY 2.1 #1: it is unreachable in the "
-            "reference too: method.py:1283 reads samples that are never saved)")
+        """Posterior approximation of phi by pooling the last tilted draws of every site
+        (reference method.py:1250-1301; there the method is unreachable because `saved_samp` is never
+        filled -- here the draws of the last `run()` are still in the device draw buffer, so no
+        `save_last_param` is needed).  Returns ``(S, m)``: the pooled covariance and mean."""
+        if self.iter == 0:
+            raise RuntimeError("Can not mix samples before at least one iteration has been done.")
+        d, K = self.dphi, self.K
+        workers = self.workers[self._shard.k_begin:self._shard.k_end]
+        n = workers[0].nsamp if workers else None
+        if n is None:
+            raise RuntimeError("No samples to mix")
+        sums = self._shard.ctx.mix_phi_sums(n)
+        if self.comm.size > 1:
+            sums = self.comm.allreduce_array(sums)
+        sm = sums[:d]
+        sS = sums[d:d + d * d].reshape(d, d, order='F')
+        sMM = sums[d + d * d:].reshape(d, d, order='F')
+        m = sm / K
+        S = (sS + n * (sMM - K * np.outer(m, m))) / (K * n - 1)
+        if out_m is None:
+            out_m = np.zeros(d)
+        if out_S is None:
+            out_S = np.zeros((d, d), order='F')
+        out_m[...] = m
+        out_S[...] = S
+        return out_S, out_m
 
     def mix_pred(self, params, param_shapes=None, param_hiers=None):
         raise NotImplementedError(

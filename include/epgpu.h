@@ -153,6 +153,12 @@ int epg_delta_snr(epg_ctx* ctx, double* stats_out);
  *   identical on every rank, so damping retries need no further exchange of matrices
  *   (epg_update_partial(df) still forms the local Qi2 = Qi + df dQi for the proposal cavities). */
 int epg_delta_sums_ex(epg_ctx* ctx, int with_norms, const double* slots, int n_slots);
+
+/* ---- Master.mix_phi, method.py:1250-1301: pool the last tilted draws of phi over the sites ----
+ * sums_out [d + 2 d*d] = sum over the local sites of [ mean_k | sum_t (x_t - mean_k)(x_t - mean_k)' | mean_k mean_k' ]
+ * of the n draws per site in the device draw buffer; the host combines (and sums over ranks):
+ *   m = sum mean_k / K,   S = (sum scatter_k + n (sum mean_k mean_k' - K m m')) / (K n - 1). */
+int epg_mix_phi_sums(epg_ctx* ctx, int n, double* sums_out);
 int epg_update_from_sums(epg_ctx* ctx, double df);
 
 /* ---- damping sweep: experiment/find_damp.py:144-174 + kl_mvn :32-51 ----

@@ -91,6 +91,18 @@ class OracleContext(object):
         b = self.a[DSUM]
         return float(b[d * d + d]), int(round(b[d * d + d + 1])), b[d * d + d + 2:].copy()
 
+    def mix_phi_sums(self, n):
+        d = self.d
+        out = np.zeros(d + 2 * d * d)
+        for k in range(self.K):
+            x = self.draws[k]
+            mk = x.mean(axis=1)
+            xc = x - mk[:, None]
+            out[:d] += mk
+            out[d:d + d * d] += (xc @ xc.T).ravel(order='F')
+            out[d + d * d:] += np.outer(mk, mk).ravel(order='F')
+        return out
+
     def update_from_sums(self, df):
         d = self.d
         Qp, rp = self._qprev

@@ -66,7 +66,10 @@ def _worker_snr(rank, world, port, ret):
         sc = td._scenario(K=9, d=5, chains=4, it=60, niter=5, seed=17, df0=orc.default_df0(9))
         m = td._master(method, sc, df_select='snr')
         info, (ms, Ss) = m.run(sc['niter'], verbose=False, seed=sc['seed'])
-        ret[rank] = dict(info=info, m=ms, S=Ss, df=list(m.history['df']), n_local=m._shard.n_local)
+        S_mix, m_mix = m.mix_phi()
+        ret[rank] = dict(info=info, m=ms, S=Ss, df=list(m.history['df']), n_local=m._shard.n_local,
+                         S_mix=S_mix.copy(), m_mix=m_mix.copy(),
+                         draws=m._shard.ctx.draws.copy(), k=(m._shard.k_begin, m._shard.k_end))
     finally:
         dist.destroy_process_group()
 
@@ -96,6 +99,19 @@ def test_two_and_three_rank_damping_selection():
             assert ret[r]['info'] == oinfo == 0
             assert relerr(ret[r]['m'], oms) < 1e-10 and relerr(ret[r]['S'], oSs) < 1e-10
             assert ret[r]['df'] == ret[0]['df']
+        # Master.mix_phi over the ranks == the reference's pooling formula (method.py:1280-1298) on all the draws
+        draws = np.concatenate([ret[r]['draws'][:ret[r]['k'][1] - ret[r]['k'][0]] for r in range(world)], axis=0)
+        K, d, n = draws.shape
+        assert K == 9
+        means = draws.mean(axis=2)
+        m_ref = means.mean(axis=0)
+        S_ref = np.zeros((d, d))
+        for k in range(K):
+            xc = draws[k] - means[k][:, None]
+            S_ref += xc @ xc.T + n * np.outer(means[k] - m_ref, means[k] - m_ref)
+        S_ref /= K * n - 1
+        for r in range(world):
+            assert relerr(ret[r]['m_mix'], m_ref) < 1e-12 and relerr(ret[r]['S_mix'], S_ref) < 1e-10
 
 
 @pytest.mark.parametrize('tag', ['runA', 'runC', 'runD', 'runF'])

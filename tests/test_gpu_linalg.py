@@ -348,3 +348,25 @@ def test_cv_moments_batched_config2(ep):
             assert bool(used[k]) == oused
             assert relerr(m[k], om) < 1e-10 and relerr(S[k], oS) < 1e-10
     ctx.close()
+
+
+@pytest.mark.parametrize('K,d,n', [(7, 5, 30), (64, 20, 800), (3, 50, 401)])
+def test_mix_phi_sums(ep, K, d, n):
+    """f4: the pooled sums behind Master.mix_phi (method.py:1280-1298) from the device draw buffer."""
+    from epstan import _lib
+    rng = np.random.RandomState(5)
+    draws = rng.standard_normal((K, d, n)) * 0.3 + rng.standard_normal((K, d, 1))
+    ctx = _lib.Context(0)
+    ctx.init_state(K, d)
+    ctx.set_draws(draws, n)
+    sums = ctx.mix_phi_sums(n)
+    means = draws.mean(axis=2)
+    sS = np.zeros((d, d)); sMM = np.zeros((d, d))
+    for k in range(K):
+        xc = draws[k] - means[k][:, None]
+        sS += xc @ xc.T
+        sMM += np.outer(means[k], means[k])
+    assert relerr(sums[:d], means.sum(axis=0)) < 1e-12
+    assert relerr(sums[d:d + d * d].reshape(d, d, order='F'), sS) < 1e-11
+    assert relerr(sums[d + d * d:].reshape(d, d, order='F'), sMM) < 1e-12
+    ctx.close()
