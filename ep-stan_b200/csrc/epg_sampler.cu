@@ -2039,6 +2039,18 @@ int epg_tilted_sample(epg_ctx* c, int k0, int k1, const uint32_t* seeds, const e
     return 0;
 }
 
+int epg_get_adapt(epg_ctx* c, int k, float* minv_out, float* eps_out) {
+    if (!c->sites || k < 0 || k >= c->K || !c->sites->last_q || c->sites->last_C < 1)
+        return epg_fail_msg(c, "epg_get_adapt: no finished sampling run");
+    epg_site_data* s = c->sites;
+    const int C = s->last_C;
+    const size_t n_lq = (size_t)c->K * C * s->Pmax;
+    EPG_CHECK(c, cudaStreamSynchronize(c->stream));
+    if (minv_out) EPG_CHECK(c, cudaMemcpy(minv_out, s->last_q + n_lq + (size_t)k * C * s->Pmax, sizeof(float) * (size_t)C * s->Pmax, cudaMemcpyDeviceToHost));
+    if (eps_out) EPG_CHECK(c, cudaMemcpy(eps_out, s->last_q + 2 * n_lq + (size_t)k * C, sizeof(float) * C, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
 int epg_reinit_sites(epg_ctx* c, int n, const int32_t* sites) {
     if (!c->sites || n < 0 || (n > 0 && !sites)) return epg_fail_msg(c, "epg_reinit_sites: bad args / no site data");
     epg_site_data* s = c->sites;

@@ -55,6 +55,7 @@ SYMBOLS = [
     ('epg_moments', C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, _c_int32_p, C.POINTER(C.c_int)]),
     ('epg_fail_sites', C.c_int, [C.c_void_p, C.c_int, _c_int32_p]),
     ('epg_reinit_sites', C.c_int, [C.c_void_p, C.c_int, _c_int32_p]),
+    ('epg_get_adapt', C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     ('epg_update_partial', C.c_int, [C.c_void_p, C.c_double]),
     ('epg_update_finish', C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
     ('epg_accept', C.c_int, [C.c_void_p]),
@@ -278,6 +279,14 @@ class Context:
     def reinit_sites(self, sites):
         sites = np.ascontiguousarray(sites, dtype=np.int32)
         self._ck(self._lib.epg_reinit_sites(self._h, len(sites), sites.ctypes.data_as(_c_int32_p)))
+
+    def get_adapt(self, k, chains, pmax):
+        """(inverse metric [chains, pmax], step size [chains]) site k's chains ended their last run with"""
+        minv = np.empty((chains, pmax), dtype=np.float32)
+        eps = np.empty(chains, dtype=np.float32)
+        self._ck(self._lib.epg_get_adapt(self._h, int(k), minv.ctypes.data_as(C.POINTER(C.c_float)),
+                                         eps.ctypes.data_as(C.POINTER(C.c_float))))
+        return minv, eps
 
     def update_partial(self, df):
         self._ck(self._lib.epg_update_partial(self._h, float(df)))

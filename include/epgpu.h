@@ -235,6 +235,10 @@ int epg_tilted_sample(epg_ctx* ctx, int k0, int k1, const uint32_t* seeds,
  * The marks are consumed by that call. */
 int epg_reinit_sites(epg_ctx* ctx, int n, const int32_t* sites);
 
+/* Diagnostics: the diagonal inverse metric [chains][Pmax] (fp32, Pmax = the largest epg_num_params of the
+ * context) and the step size [chains] site k's chains ended their last run with (what carry_adapt carries over). */
+int epg_get_adapt(epg_ctx* ctx, int k, float* minv_out, float* eps_out);
+
 /* Options.  "carry_adapt" (default 1): a run with init_mode 2 (init_prev) starts its warm-up from the metric
  * and step size the previous run of the same chain ended with, instead of Stan's unit metric and step size 1
  * (an extension in the spirit of init_prev, method.py:404-406; the warm-up itself -- dual averaging, variance
