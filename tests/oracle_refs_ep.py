@@ -1,14 +1,18 @@
 """Oracle references for posterior parity (check (c)) on BASELINE shapes.
 
-    python tests/oracle_refs_ep.py cfg3      # ~10 min on 8 cores
-    python tests/oracle_refs_ep.py cfg4s     # config-4 subset (first 32 sites): ~1 h on 8 cores
+    python tests/oracle_refs_ep.py cfg3            # oracle EP: ~20 min on 8 cores
+    python tests/oracle_refs_ep.py cfg3 8 target   # + the full-data posterior by the oracle NUTS (128 000 rows: hours)
+    python tests/oracle_refs_ep.py cfg4s           # config-4 subset (first 16 sites, 5 EP iterations): ~1 h on 8 cores
 
 For a workload this caches in tests/golden/ep_ref_<tag>.npz
   * the oracle EP run (oracle NUTS per site: oracle/nuts.py on oracle/density.py, oracle moment matching and
     updates: oracle/ep_linalg.py) on the SAME data the GPU test uses (bench.simulate_problem, seed 100), with
     the same seed-independent settings (chains, iterations, damping rule), and
-  * the full-data posterior of phi by the oracle NUTS ("target", as experiment/fit.py --run_target does it
-    with one multi-group Stan program), cfg3 only.
+  * optionally (argument `target`) the full-data posterior of phi by the oracle NUTS ("target", as
+    experiment/fit.py --run_target does it with one multi-group Stan program).  It takes hours on the
+    128 000-row problem; the GPU test uses the GPU full-data sampler for that comparison instead, which
+    tests/test_gpu_experiment.py::test_fit_results_against_oracle_posterior pins to the oracle on a problem
+    the oracle finishes in seconds.
 Both are fp64 CPU runs; the GPU results must agree with them within the KL tolerances stated in
 tests/test_gpu_parity_ep.py.  PyStan itself is not installable here: parity of the sampler is
 pinned on this restatement, the moment/update path on the reference itself.
@@ -32,7 +36,7 @@ from oracle import nuts                   # noqa: E402
 # tag: (model, K_total simulated, K used, n_k, D, chains, siter, EP iterations)
 CASES = {
     'cfg3': ('m1b', 64, 64, 2000, 19, 8, 200, 12),
-    'cfg4s': ('m3b', 1024, 32, 5000, 49, 4, 200, 8),
+    'cfg4s': ('m3b', 1024, 16, 5000, 49, 4, 200, 5),
 }
 
 
@@ -125,7 +129,7 @@ def main():
     tag = sys.argv[1]
     procs = int(sys.argv[2]) if len(sys.argv) > 2 else (os.cpu_count() or 1)
     out = {}
-    if tag == 'cfg3':
+    if len(sys.argv) > 3 and sys.argv[3] == 'target':
         out.update(oracle_target(tag, procs))
     out.update(oracle_ep(tag, procs))
     path = os.path.join(HERE, 'golden', 'ep_ref_%s.npz' % tag)
