@@ -57,6 +57,9 @@ struct epg_site_data {
     CUtensorMap tmap;                   // TMA descriptor of Xb: box 64 x 128 rows, 128-byte swizzle
     bool tc_ok = false;                 // tensor-core pass usable (single group, D+1 <= 64)
     int use_tc = 1;                     // option (epg_set_option "use_tc")
+    double* tstats = nullptr;           // [K][2][P] per-site mean and sum of squared deviations of the transformed
+    size_t tstats_bytes = 0;            //     parameters over the last run's draws (option "param_stats", Master.mix_pred)
+    int param_stats = 0;
     int carry_adapt = 1;                // option "carry_adapt": init_prev runs start from the previous run's adapted metric / step size
     int pp_mode = 0;                    // option "pingpong": 0 never (default), 1 when sites > SMs and L2-resident, 2 always
     float* y = nullptr;                 // [N]
@@ -84,7 +87,7 @@ struct epg_site_data {
 void epg_sites_free(epg_ctx* c) {
     epg_site_data* s = c->sites;
     if (!s) return;
-    cudaFree(s->xmean); cudaFree(s->order); cudaFree(s->reinit);
+    cudaFree(s->xmean); cudaFree(s->order); cudaFree(s->reinit); cudaFree(s->tstats);
     cudaFree(s->X); cudaFree(s->Xb); cudaFree(s->y); cudaFree(s->row0); cudaFree(s->grp_ptr); cudaFree(s->grp_rows);
     cudaFree(s->chain_mem); cudaFree(s->last_q); cudaFree(s->omega); cudaFree(s->out); cudaFree(s->ld_buf);
     delete s;
@@ -184,6 +187,7 @@ enum {
     V_NHOT,                       // ---- vectors below are always in global memory ----
     V_WMEAN = V_NHOT, V_WM2,      // Welford accumulators
     V_RS0, V_RQ0, V_RS1, V_RQ1,   // split-Rhat sums / sums of squares per half
+    V_TREF, V_TS, V_TQ,           // transformed parameters (alpha, beta): first draw, sums and sums of squares about it
     V_STACK                       // + 4*level : psl, rho, qprop, gprop
 };
 #define NVEC (V_STACK + 4 * MAXDEPTH_CAP)
@@ -229,6 +233,7 @@ struct SamplerArgs {
     const uint32_t* seeds;
     // outputs
     double* draws; int n_draws;     // [K][d][n]
+    double* tstats;                 // [K][2][P] or nullptr (see epg_site_data)
     double* out;                    // [K][8]: mean eps, max rhat, n_leapfrog, n_divergent, clk chain, clk lik, ticks, -
     int k0;
     // shared-memory plan
@@ -966,6 +971,27 @@ __device__ void end_transition(const CX& x, ChainS& s, int c_local, int k_global
             }
         }
         s.eps_sum += s.eps;
+        if (a.tstats) {
+            // transformed parameters of the Stan programs (m1b.stan:30-36 ...): slot i of q maps to
+            // phi_i | alpha_j = [mu_a +] eta_j sigma_a | beta_ji = [mu_b,i +] etb_ji sigma_b,i
+            float* tr = x.v(V_TREF); float* ts = x.v(V_TS); float* tq = x.v(V_TQ);
+            const int D = x.D, J = x.J, d = a.d;
+            const bool four = model_four(a.model);
+            const int ia = four ? 1 : 0, ib = four ? 2 + D : 1;
+            for (int i = x.lane; i < x.p; i += 32) {
+                float T;
+                if (i < d) T = qs[i];
+                else if (i < d + J) T = qs[i] * __expf(qs[ia]) + (four ? qs[0] : 0.0f);
+                else {
+                    const int e = i - d - J;
+                    const int col = a.model == EPG_M2B ? e : e % D;
+                    const float lsb = a.model == EPG_M2B ? qs[ib] : qs[ib + col];
+                    T = qs[i] * __expf(lsb) + (four ? qs[2 + col] : 0.0f);
+                }
+                if (t == 0) { tr[i] = T; ts[i] = 0.0f; tq[i] = 0.0f; }
+                else { const float dv = T - tr[i]; ts[i] += dv; tq[i] += dv * dv; }
+            }
+        }
     }
     __syncwarp();
     s.iter += 1;
@@ -1304,6 +1330,28 @@ __device__ void site_analytics(const SamplerArgs& a, const SiteView& sv, const C
         for (int e = lane; e < a.d * per; e += 32) {
             const int i = e / per, t = e - i * per;
             dst[(size_t)i * a.n_draws + c * per + t] = NAN;
+        }
+    }
+    if (a.tstats) {
+        double* to = a.tstats + (size_t)sv.k * 2 * a.P;
+        for (int i = lane; i < p; i += 32) {
+            double msum = 0.0;
+            int m = 0;
+            for (int c = 0; c < C; ++c) {
+                if (cs[c].phase != PH_DONE) continue;
+                msum += (double)cvec(a, sv, c, V_TREF)[i] + (double)cvec(a, sv, c, V_TS)[i] / per;
+                ++m;
+            }
+            const double mean = m ? msum / m : NAN;
+            double ssd = 0.0;
+            for (int c = 0; c < C; ++c) {
+                if (cs[c].phase != PH_DONE) continue;
+                const double s1 = cvec(a, sv, c, V_TS)[i], s2 = cvec(a, sv, c, V_TQ)[i];
+                const double mc = (double)cvec(a, sv, c, V_TREF)[i] + s1 / per;
+                ssd += (s2 - s1 * s1 / per) + per * (mc - mean) * (mc - mean);
+            }
+            to[i] = mean;
+            to[a.P + i] = m ? ssd : NAN;
         }
     }
     if (lane == 0) {
@@ -1825,6 +1873,11 @@ int epg_set_option(epg_ctx* c, const char* name, double value) {
         c->sites->use_tc = value != 0.0;
         return 0;
     }
+    if (strcmp(name, "param_stats") == 0) {
+        if (!c->sites) return epg_fail_msg(c, "epg_set_option(param_stats): upload the sites first");
+        c->sites->param_stats = value != 0.0;
+        return 0;
+    }
     if (strcmp(name, "carry_adapt") == 0) {
         if (!c->sites) return epg_fail_msg(c, "epg_set_option(carry_adapt): upload the sites first");
         c->sites->carry_adapt = value != 0.0;
@@ -1870,6 +1923,11 @@ static int fill_args(epg_ctx* c, SamplerArgs& a, int C, int CP, int n_sites = 1,
     EPG_CHECK(c, epg_reserve((void**)&s->out, &s->out_bytes, sizeof(double) * (size_t)c->K * 8 + sizeof(uint32_t) * ((size_t)c->K + 4)));
     a.chain_mem = s->chain_mem; a.last_q = s->last_q; a.omega = s->omega; a.out = s->out;
     a.last_minv = s->last_q + n_lq; a.last_eps = s->last_q + 2 * n_lq; a.carry_adapt = s->carry_adapt;
+    a.tstats = nullptr;
+    if (s->param_stats) {
+        EPG_CHECK(c, epg_reserve((void**)&s->tstats, &s->tstats_bytes, sizeof(double) * (size_t)c->K * 2 * s->Pmax));
+        a.tstats = s->tstats;
+    }
     a.use_tc = (s->tc_ok && s->use_tc && C <= tc::NCH) ? 1 : 0;
     // More sites than SMs: the ping-pong kernel (two sites per persistent CTA) if both per-site blocks fit.
     a.tc_nst = tc::NST;
@@ -2038,6 +2096,24 @@ int epg_tilted_sample(epg_ctx* c, int k0, int k1, const uint32_t* seeds, const e
     }
     return 0;
 }
+
+int epg_get_param_stats(epg_ctx* c, int k0, int k1, double* mean_out, double* ssd_out) {
+    if (!c->sites || !c->sites->tstats || k0 < 0 || k1 > c->K || k0 >= k1 || !mean_out || !ssd_out)
+        return epg_fail_msg(c, "epg_get_param_stats: enable option param_stats before sampling");
+    epg_site_data* s = c->sites;
+    const size_t P = s->Pmax;
+    std::vector<double> h((size_t)(k1 - k0) * 2 * P);
+    EPG_CHECK(c, cudaMemcpyAsync(h.data(), s->tstats + (size_t)k0 * 2 * P, sizeof(double) * h.size(), cudaMemcpyDeviceToHost, c->stream));
+    EPG_CHECK(c, cudaStreamSynchronize(c->stream));
+    for (int k = 0; k < k1 - k0; ++k)
+        for (size_t i = 0; i < P; ++i) {
+            mean_out[(size_t)k * P + i] = h[(size_t)k * 2 * P + i];
+            ssd_out[(size_t)k * P + i] = h[(size_t)k * 2 * P + P + i];
+        }
+    return 0;
+}
+
+int epg_max_params(epg_ctx* c) { return c->sites ? c->sites->Pmax : -1; }
 
 int epg_get_adapt(epg_ctx* c, int k, float* minv_out, float* eps_out) {
     if (!c->sites || k < 0 || k >= c->K || !c->sites->last_q || c->sites->last_C < 1)

@@ -55,6 +55,8 @@ SYMBOLS = [
     ('epg_moments', C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, _c_int32_p, C.POINTER(C.c_int)]),
     ('epg_fail_sites', C.c_int, [C.c_void_p, C.c_int, _c_int32_p]),
     ('epg_reinit_sites', C.c_int, [C.c_void_p, C.c_int, _c_int32_p]),
+    ('epg_get_param_stats', C.c_int, [C.c_void_p, C.c_int, C.c_int, _c_double_p, _c_double_p]),
+    ('epg_max_params', C.c_int, [C.c_void_p]),
     ('epg_get_adapt', C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     ('epg_update_partial', C.c_int, [C.c_void_p, C.c_double]),
     ('epg_update_finish', C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
@@ -279,6 +281,15 @@ class Context:
     def reinit_sites(self, sites):
         sites = np.ascontiguousarray(sites, dtype=np.int32)
         self._ck(self._lib.epg_reinit_sites(self._h, len(sites), sites.ctypes.data_as(_c_int32_p)))
+
+    def param_stats(self, k0=0, k1=None):
+        """(mean, sum of squared deviations), each [k1-k0, Pmax], of the transformed site parameters over
+        the draws of the last sampling run (option 'param_stats')"""
+        k1 = self.K if k1 is None else k1
+        P = int(self._lib.epg_max_params(self._h))
+        mean = np.empty((k1 - k0, P)); ssd = np.empty((k1 - k0, P))
+        self._ck(self._lib.epg_get_param_stats(self._h, k0, k1, _dp(mean), _dp(ssd)))
+        return mean, ssd
 
     def get_adapt(self, k, chains, pmax):
         """(inverse metric [chains, pmax], step size [chains]) site k's chains ended their last run with"""

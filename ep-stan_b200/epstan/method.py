@@ -884,6 +884,10 @@ class Master(object):
             self._push_state(with_cavity=True)
         self.history = dict(df=[], attempts=[], snr=[], n_ok=[], rhat_sites=[], n_fail=[], rejected=[])
         local_workers = self.workers[sh.k_begin:sh.k_end]
+        if self.builtin and sh.n_local:
+            # moments of the transformed site parameters for mix_pred (the reference saves the samples:
+            # method.py:1012-1016 `save_last_param`)
+            ctx.set_option('param_stats', 1 if save_last_param else 0)
 
         for cur_iter in range(niter):
             self.iter += 1
@@ -1033,7 +1037,116 @@ class Master(object):
         out_S[...] = S
         return out_S, out_m
 
-    def mix_pred(self, params, param_shapes=None, param_hiers=None):
-        raise NotImplementedError(
-            "mix_pred is outside the EP inner loop (SURVEY 2.1 #1: the reference reads "
-            "`workers[k].fit`, which is never assigned: method.py:1368)")
+    # ---- parameter slots of the built-in models in a site's sampled vector q = [phi | eta | etb] ----
+    def _param_slots(self, k, par):
+        """(first slot, shape) of transformed parameter `par` of site k (see epg_get_param_stats)."""
+        w = self.workers[k]
+        fam = self.site_model.family
+        D = w.X.shape[1]
+        J = 1 if self.site_model.single_group else int(w.A['J'])
+        d = self.dphi
+        if par == 'phi':
+            return 0, (d,)
+        if par == 'alpha':
+            return d, (J,)
+        if par == 'beta':
+            if fam == 'm1b':
+                return 1, (D,)
+            if fam == 'm2b':
+                return d + J, (D,)
+            return d + J, (J, D)
+        raise ValueError("built-in models provide 'phi', 'alpha' and 'beta' (got {})".format(repr(par)))
+
+    def mix_pred(self, params, smap=None, param_shapes=None):
+        """Mean and variance of site parameters by pooling the last tilted draws of every site
+        (reference method.py:1304-1478; unreachable there, `workers[k].fit` is never assigned).
+
+        For the built-in models the sampler accumulates the moments of the transformed parameters
+        ``'alpha'`` and ``'beta'`` (and ``'phi'``) on the device when the last ``run`` was given
+        ``save_last_param``; `params`, `smap`, `param_shapes` and the pooling rules are the reference's:
+        ``smap[k]`` maps the indices of site k's parameter to the global one (None: every site
+        contributes to the whole parameter)."""
+        if self.iter == 0:
+            raise RuntimeError("Can not mix samples before at least one iteration has been done.")
+        if not self.builtin:
+            raise NotImplementedError("mix_pred needs the built-in sampler's parameter statistics")
+        if isinstance(params, str):
+            only_one_param = True
+            params, smap, param_shapes = [params], [smap], [param_shapes]
+        else:
+            only_one_param = False
+        sh = self._shard
+        try:
+            mean_l, ssd_l = sh.ctx.param_stats(0, sh.n_local)
+        except Exception as e:
+            raise RuntimeError("No parameter statistics: call run(..., save_last_param=[...]) first ({})".format(e))
+        if self.comm.size > 1:
+            mean_all = self.comm.allgather_sites(mean_l.T, self.K, 1).T
+            ssd_all = self.comm.allgather_sites(ssd_l.T, self.K, 1).T
+        else:
+            mean_all, ssd_all = mean_l, ssd_l
+        K = self.K
+        ns = np.array([w.nsamp for w in self.workers], dtype=np.int64)
+        ms_all, vs_all = [], []
+        for par in params:
+            ms, vs = [], []
+            for k in range(K):
+                o, shp = self._param_slots(k, par)
+                cnt = int(np.prod(shp))
+                ms.append(mean_all[k, o:o + cnt].reshape(shp))
+                vs.append(ssd_all[k, o:o + cnt].reshape(shp))          # sum of squared deviations
+            ms_all.append(ms)
+            vs_all.append(vs)
+        mean, var = pool_site_moments(ns, ms_all, vs_all, smap, param_shapes)
+        if only_one_param:
+            return mean[0], var[0]
+        return mean, var
+
+
+def pool_site_moments(ns, ms_all, vs_all, smap, param_shapes):
+    """The pooling rules of the reference's `Master.mix_pred` (method.py:1375-1471) on per-site moments:
+    ns[k] draws, ms_all[ip][k] the mean and vs_all[ip][k] the sum of squared deviations of parameter ip in
+    site k; smap[ip] None (every site contributes to the whole parameter) or a per-site index into the
+    global parameter of shape param_shapes[ip]."""
+    K = len(ns)
+    mean, var = [], []
+    for ip in range(len(ms_all)):
+        ms, vs = ms_all[ip], vs_all[ip]
+        sit = smap[ip] if smap is not None else None
+        if sit is None:
+            ms_a, vs_a = np.array(ms), np.array(vs)
+            n = ns.sum()
+            mc = (ms_a.T * ns).T.sum(axis=0) / n
+            vc = ((((ms_a - mc) ** 2).T * ns).T + vs_a).sum(axis=0) / (n - 1)
+        else:
+            par_shape = param_shapes[ip]
+            count = np.zeros(par_shape)
+            for k in range(K):
+                count[sit[k]] += 1
+            if np.count_nonzero(count) != count.size:
+                raise ValueError("Arg. `smap` does not fill the parameter")
+            onecont = count == 1
+            mc = np.zeros(par_shape)
+            vc = np.zeros(par_shape)
+            if np.all(onecont):
+                for k in range(K):
+                    mc[sit[k]] = ms[k]
+                    vc[sit[k]] = vs[k] / (ns[k] - 1)
+            else:
+                nc = np.zeros(par_shape, dtype=np.int64)
+                for k in range(K):
+                    nc[sit[k]] += ns[k]
+                    mc[sit[k]] += ns[k] * ms[k]
+                mc /= nc
+                for k in range(K):
+                    vc[sit[k]] += ns[k] * (np.asarray(ms[k] - mc[sit[k]]) ** 2) + vs[k]
+                vc /= (nc - 1)
+                if np.any(onecont):
+                    # (method.py:1464-1469: as soon as one index has a single contribution the reference
+                    #  re-assigns every site's own moments in site order; kept as it is)
+                    for k in range(K):
+                        mc[sit[k]] = ms[k]
+                        vc[sit[k]] = vs[k] / (ns[k] - 1)
+        mean.append(mc)
+        var.append(vc)
+    return mean, var

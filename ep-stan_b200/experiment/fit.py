@@ -11,7 +11,7 @@ Group ``<model_name>`` is a simulated model in ./models (m1b, m2b, m3b, m4b, m5b
 EP branch (``--run_ep``) is the reference's (fit.py:279-459) on the GPU Master.
 ``--run_full`` / ``--run_target`` sample the full-data posterior with the same
 built-in NUTS sampler (one site holding every group, cavity = prior);
-``--mix`` is outside the EP path and not provided; ``--run_consensus`` pools per-site draws on one GPU.
+``--mix`` pools the last tilted draws (Master.mix_phi / mix_pred); ``--run_consensus`` pools per-site draws on one GPU.
 
 Results go to ./results with the reference's file names and npz keys
 (res_d_<model>.npz: m_s_ep, S_s_ep, time_s_ep, mstepsize_s_ep, mrhat_s_ep;
@@ -120,6 +120,25 @@ def _full_posterior_draws(model_name, data, prior, chains, siter, seed):
     return w.saved_samp['phi'], w
 
 
+def _param_maps(phiers, J, K, Nj_k):
+    """Which entries of each inferred parameter a site contributes to (reference fit.py:763-815,
+    `_create_pmaps`): None for a shared parameter; for a parameter with a hierarchical dimension `ih`, per
+    site an index into that dimension -- the site's own group (K == J) or its block of merged groups."""
+    maps = []
+    for ih in phiers:
+        if ih is None:
+            maps.append(None)
+        elif K == J:
+            maps.append(np.arange(K) if ih == 0 else
+                        [tuple(k if a == ih else slice(None) for a in range(ih + 1)) for k in range(K)])
+        else:
+            starts = np.concatenate(([0], np.cumsum(Nj_k)))
+            blocks = [slice(int(starts[k]), int(starts[k + 1])) for k in range(K)]
+            maps.append(blocks if ih == 0 else
+                        [tuple(b if a == ih else slice(None) for a in range(ih + 1)) for b in blocks])
+    return maps
+
+
 def _site_master(model_name, data, J, K, options):
     """Master over K sites built from the J simulated groups (reference fit.py:300-345)."""
     if K < 2:
@@ -202,11 +221,10 @@ def main(model_name, conf, ret_master=False):
         print("Distributed method")
         iters_to_run = EP_DEFAULT_ITERS_TO_RUN(K) if conf.iter is None else conf.iter
         df0 = default_df0(K) if conf.damp is None else conf.damp
-        if conf.mix:
-            raise NotImplementedError("--mix feeds Master.mix_pred, which is outside the EP path")
         epstan_options = dict(prior=prior, prec_estim=conf.prec_estim, df0=df0, init_site=None,
                               chains=conf.chains, iter=conf.siter, warmup=None, thin=1)
         epstan_master = _site_master(model_name, data, J, K, epstan_options)
+        pmaps = _param_maps(phiers, J, K, None if K == J else distribute_groups(J, K, data.Nj)[1])
         if ret_master:
             print("Returning epstan.Master")
             return epstan_master
@@ -214,7 +232,7 @@ def main(model_name, conf, ret_master=False):
         S_ep_init, m_ep_init = epstan_master.cur_approx()
         print("Run distributed EP algorithm for {} iterations.".format(iters_to_run))
         info, (m_s_ep, S_s_ep), (time_s_ep, mstepsize_s_ep, mrhat_s_ep, othertimes) = epstan_master.run(
-            iters_to_run, return_analytics=True, save_last_param=None, seed=conf.seed_ep)
+            iters_to_run, return_analytics=True, save_last_param=pnames if conf.mix else None, seed=conf.seed_ep)
         time_s_ep = np.insert(time_s_ep.cumsum(), 0, 0.0)
         S_s_ep = np.concatenate((S_ep_init[None, :, :], S_s_ep), axis=0)
         m_s_ep = np.concatenate((m_ep_init[None, :], m_s_ep), axis=0)
@@ -227,9 +245,19 @@ def main(model_name, conf, ret_master=False):
                          othertimes=othertimes, last_iter=epstan_master.iter)
                 print("Uncomplete distributed model results saved.")
             raise RuntimeError('epstan algorithm failed with error code: {}'.format(info))
+        extra = {}
+        if conf.mix:
+            # final approximation by mixing the last samples of all the sites (reference fit.py:408-420)
+            print("Form the final approximation by mixing the last samples from all the sites.")
+            S_mix, m_mix = epstan_master.mix_phi()
+            pms, pvars = epstan_master.mix_pred(list(pnames), pmaps, list(pshapes))
+            extra = dict(othertimes=othertimes, m_phi_ep=m_mix, S_phi_ep=S_mix)
+            for name, pm, pv in zip(pnames, pms, pvars):
+                extra['m_' + name + '_ep'] = pm
+                extra['v_' + name + '_ep'] = pv
         if conf.save_res:
             np.savez(_res_file('res_d', model_name, conf), conf=conf.__dict__, m_s_ep=m_s_ep, S_s_ep=S_s_ep,
-                     time_s_ep=time_s_ep, mstepsize_s_ep=mstepsize_s_ep, mrhat_s_ep=mrhat_s_ep)
+                     time_s_ep=time_s_ep, mstepsize_s_ep=mstepsize_s_ep, mrhat_s_ep=mrhat_s_ep, **extra)
             print("Distributed model results saved.")
         del epstan_master
         print("Done with distributed method")
@@ -322,7 +350,7 @@ CONF_HELP = dict(
     run_consensus='run consensus MC method', run_target='run target approximation',
     iter='number of distributed EP iterations', siter='sampler iterations in each major iteration',
     target_siter='sampler iterations for the target approximation', chains='number of chains used in sampling',
-    damp='damping factor constant', mix='mix last iteration samples (not provided)',
+    damp='damping factor constant', mix='mix last iteration samples',
     prec_estim='estimate method for tilted distribution precision matrix: sample or olse',
     seed_data='seed for data simulation', seed_ep='seed for distributed EP sampling',
     seed_full='seed for full sampling', seed_cons='seed for consensus sampling',

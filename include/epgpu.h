@@ -235,6 +235,15 @@ int epg_tilted_sample(epg_ctx* ctx, int k0, int k1, const uint32_t* seeds,
  * The marks are consumed by that call. */
 int epg_reinit_sites(epg_ctx* ctx, int n, const int32_t* sites);
 
+/* ---- Master.mix_pred, method.py:1304-1478: moments of the site parameters over the last draws ----
+ * With option "param_stats" = 1 the sampler accumulates, for every sampled slot i of a site's parameter vector
+ * q = [phi (d) | eta (J) | etb], the TRANSFORMED parameter of the Stan programs (m1b.stan:30-36 ...):
+ * phi_i | alpha_j = [mu_a +] eta_j sigma_a | beta_ji = [mu_b,i +] etb_ji sigma_b,i.
+ * epg_get_param_stats returns per site the mean and the sum of squared deviations over all retained draws of all
+ * chains, [k1-k0][Pmax] each (Pmax = epg_max_params; slots beyond a site's epg_num_params are undefined). */
+int epg_get_param_stats(epg_ctx* ctx, int k0, int k1, double* mean_out, double* ssd_out);
+int epg_max_params(epg_ctx* ctx);
+
 /* Diagnostics: the diagonal inverse metric [chains][Pmax] (fp32, Pmax = the largest epg_num_params of the
  * context) and the step size [chains] site k's chains ended their last run with (what carry_adapt carries over). */
 int epg_get_adapt(epg_ctx* ctx, int k, float* minv_out, float* eps_out);

@@ -211,6 +211,49 @@ def gen_cv(ep, out):
         out['cv_%s_fallback_used' % tag] = np.array(used)
 
 
+def mix_case(seed=61):
+    """Synthetic per-site draws for Master.mix_phi / mix_pred (tests regenerate them from the seed)."""
+    rng = np.random.RandomState(seed)
+    K, d, D = 3, 4, 2
+    Jk = [2, 1, 3]
+    n = [40, 50, 60]
+    sites = []
+    for k in range(K):
+        sites.append(dict(phi=rng.standard_normal((45, d)) * 0.3 + rng.standard_normal(d),   # (one n: the device draw buffer)
+                          beta=rng.standard_normal((n[k], D)) + 0.5 * k,
+                          alpha=rng.standard_normal((n[k], Jk[k])) * 0.5 + k,
+                          gamma=rng.standard_normal((n[k], 2)) + k))
+    starts = np.concatenate(([0], np.cumsum(Jk)))
+    smap_alpha = [slice(int(starts[k]), int(starts[k + 1])) for k in range(K)]
+    smap_gamma = [np.array([0, 1]), np.array([1, 2]), np.array([2, 3])]        # overlapping: indices 1, 2 twice
+    return sites, Jk, smap_alpha, smap_gamma
+
+
+def gen_mix(ep, out):
+    """The unmodified reference's Master.mix_phi / mix_pred (method.py:1250-1478) on mocked workers (the
+    methods only read `workers[k].saved_samp` / `workers[k].fit`, which the reference never fills itself)."""
+    import types
+    sites, Jk, smap_alpha, smap_gamma = mix_case()
+
+    class Fit(object):
+        def __init__(self, samples):
+            self.samples = samples
+            self.model_pars = list(samples.keys())
+            self.par_dims = [list(samples[p].shape[1:]) for p in self.model_pars]
+
+        def extract(self, pars):
+            return {pars: self.samples[pars].copy()}
+    workers = [types.SimpleNamespace(fit=Fit({p: s[p] for p in ('beta', 'alpha', 'gamma')}),
+                                     saved_samp={'phi': np.asfortranarray(s['phi'].copy())}) for s in sites]
+    dummy = types.SimpleNamespace(iter=1, K=len(sites), dphi=sites[0]['phi'].shape[1], workers=workers)
+    S, m = ep.method.Master.mix_phi(dummy)
+    out['mix_phi_S'], out['mix_phi_m'] = S, m
+    means, vars_ = ep.method.Master.mix_pred(dummy, ['beta', 'alpha', 'gamma'], [None, smap_alpha, smap_gamma],
+                                             [None, (sum(Jk),), (4,)])
+    for name, mm, vv in zip(('beta', 'alpha', 'gamma'), means, vars_):
+        out['mix_%s_m' % name], out['mix_%s_v' % name] = mm, vv
+
+
 def gen_misc(ep, out):
     import fit as ref_fit
     import find_damp as ref_fd
@@ -250,7 +293,7 @@ def main():
     ep = import_reference()
     os.makedirs(OUT, exist_ok=True)
     for name, fn in (('linalg', gen_linalg), ('worker', gen_worker),
-                     ('master', gen_master), ('cv', gen_cv), ('misc', gen_misc),
+                     ('master', gen_master), ('cv', gen_cv), ('mix', gen_mix), ('misc', gen_misc),
                      ('models', gen_models)):
         out = {}
         fn(ep, out)

@@ -117,3 +117,28 @@ def test_fit_results_against_oracle_posterior(fit, tmp_path, monkeypatch):
     check(ep['m_s_ep'][-1], ep['S_s_ep'][-1], 0.6, 0.5, 'distributed EP, 8 iterations')
     # and EP ends closer to the posterior than it started
     assert orc.kl_mvn(om, oS, ep['m_s_ep'][-1], ep['S_s_ep'][-1]) < orc.kl_mvn(om, oS, ep['m_s_ep'][0], ep['S_s_ep'][0])
+
+
+@pytest.mark.parametrize('model,K', [('m1b', 4), ('m4b', 8)])
+def test_fit_mix_option(fit, tmp_path, monkeypatch, model, K):
+    """fit.py --mix (reference fit.py:408-420, 430-447): the final approximation of phi and of the inferred
+    parameters alpha, beta by mixing the last samples of every site; K < J (merged groups) and K == J."""
+    monkeypatch.setattr(fit, 'RES_PATH', str(tmp_path))
+    conf = fit.configurations(J=8, D=3, K=K, npg=40, run_ep=True, iter=4, siter=200, chains=4, mix=True)
+    fit.main(model, conf)
+    res = np.load(os.path.join(str(tmp_path), 'res_d_%s.npz' % model), allow_pickle=True)
+    tv = np.load(os.path.join(str(tmp_path), 'true_vals_%s.npz' % model), allow_pickle=True)
+    d = {'m1b': 4, 'm4b': 8}[model]
+    assert res['m_phi_ep'].shape == (d,) and res['S_phi_ep'].shape == (d, d)
+    assert np.all(np.linalg.eigvalsh(res['S_phi_ep']) > 0)
+    assert res['m_alpha_ep'].shape == (8,) and res['v_alpha_ep'].shape == (8,) and np.all(res['v_alpha_ep'] > 0)
+    bshape = (3,) if model == 'm1b' else (8, 3)
+    assert res['m_beta_ep'].shape == bshape and np.all(res['v_beta_ep'] > 0)
+    # the mixed phi agrees with the EP approximation of the last iteration (same information, pooled draws)
+    sd = np.sqrt(np.diag(res['S_s_ep'][-1]))
+    assert np.all(np.abs(res['m_phi_ep'] - res['m_s_ep'][-1]) < 3.0 * sd)
+    # the group intercepts are recovered in the right slots (K < J: merged groups map to blocks of alpha):
+    # 40 observations per group, 4 damped EP iterations -> strongly correlated with the truth, a few sd off
+    z = (res['m_alpha_ep'] - tv['alpha']) / np.sqrt(res['v_alpha_ep'])
+    assert np.corrcoef(res['m_alpha_ep'], tv['alpha'])[0, 1] > 0.9, (res['m_alpha_ep'], tv['alpha'])
+    assert np.sqrt(np.mean(z ** 2)) < 4.0, z

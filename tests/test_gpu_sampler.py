@@ -225,6 +225,50 @@ def test_reinit_sites_overrides_init_prev():
     assert np.all(np.isfinite(b1)) and np.all(np.isfinite(c1))
 
 
+@pytest.mark.parametrize('model,J,n,D', [('m1b', 1, 300, 4), ('m4b', 3, 240, 3), ('m2b', 2, 300, 3)])
+def test_param_stats_for_mix_pred(model, J, n, D):
+    """f4: the on-device moments of the transformed site parameters (epg_get_param_stats, what Master.mix_pred
+    pools): the phi slots against the retained draws themselves, alpha / beta against the fp64 oracle NUTS
+    (transformed per draw as the Stan programs do) within 5 Monte Carlo standard errors."""
+    site = synth.make_site(model, n, D, J, seed=23)
+    ctx = make_ctx(model, [site])
+    ctx.set_option('param_stats', 1)
+    C, iters, warm = 8, 700, 300
+    ctx.tilted_sample([11], C, iters, warm)
+    per = iters - warm
+    ntot = C * per
+    mean, ssd = ctx.param_stats()
+    d = site['d']
+    p = ctx.num_params(0)
+    dr = ctx.get_draws(ntot)[0]                                        # (d, n)
+    assert np.max(np.abs(mean[0, :d] - dr.mean(axis=1))) < 1e-5 * max(1.0, np.max(np.abs(dr)))
+    ssd_ref = ((dr - dr.mean(axis=1, keepdims=True)) ** 2).sum(axis=1)
+    assert np.max(np.abs(ssd[0, :d] - ssd_ref) / ssd_ref) < 2e-3        # (fp32 running sums)
+    # alpha, beta: oracle NUTS on the same site, transformed as in the Stan programs
+    td = dens.TiltedDensity(model, site['X'], site['y'], site['mu'], site['Omega'], j_ind=site['j_ind'], J=J)
+    res = nuts.sample(lambda q: tuple(v[0] for v in td.lp_grad(q[None])), td.p, chains=8, n_iter=1500, seed=5)
+    q = res['draws']
+    four = model in ('m4b', 'm5b')
+    ia, ib = (1, 2 + D) if four else (0, 1)
+    alpha = q[:, d:d + J] * np.exp(q[:, [ia]]) + (q[:, [0]] if four else 0.0)
+    if model == 'm1b':
+        T = alpha
+    elif model == 'm2b':
+        T = np.concatenate([alpha, q[:, d + J:d + J + D] * np.exp(q[:, [ib]])], axis=1)
+    else:
+        etb = q[:, d + J:].reshape(-1, J, D)
+        beta = etb * np.exp(q[:, None, ib:ib + D]) + (q[:, None, 2:2 + D] if four else 0.0)
+        T = np.concatenate([alpha, beta.reshape(len(q), -1)], axis=1)
+    assert T.shape[1] == p - d
+    om, osd = T.mean(axis=0), T.std(axis=0)
+    gm = mean[0, d:p]
+    gsd = np.sqrt(ssd[0, d:p] / (ntot - 1))
+    mcse = osd * np.sqrt(1.0 / 400 + 1.0 / 400)                        # ~400 effective draws on either side
+    assert np.all(np.abs(gm - om) < 5 * mcse), (gm - om) / mcse
+    assert np.all(np.abs(np.log(gsd / osd)) < 0.35), gsd / osd
+    ctx.close()
+
+
 _ep_problem = oracle_refs.ep_problem
 
 
