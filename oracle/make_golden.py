@@ -252,6 +252,19 @@ def gen_mix(ep, out):
                                              [None, (sum(Jk),), (4,)])
     for name, mm, vv in zip(('beta', 'alpha', 'gamma'), means, vars_):
         out['mix_%s_m' % name], out['mix_%s_v' % name] = mm, vv
+    # experiment/fit.py:763-815 `_create_pmaps`: which entries of a parameter each site fills, recorded as the
+    # flat indices every site's map selects
+    import fit as ref_fit
+    for tag, J, K, Ns in (('KeqJ', 6, 6, None), ('KltJ', 6, 3, [2, 1, 3])):
+        phiers, shapes = (0, None, 0), ((J,), (2,), (J, 2))
+        pmaps = ref_fit._create_pmaps(phiers, J, K, Ns)
+        for ip, (pm, shp) in enumerate(zip(pmaps, shapes)):
+            if pm is None:
+                continue
+            arr = np.arange(int(np.prod(shp))).reshape(shp)
+            sel = [np.atleast_1d(arr[pm[k]]).ravel() for k in range(K)]
+            out['pmap_%s_%d_idx' % (tag, ip)] = np.concatenate(sel)
+            out['pmap_%s_%d_len' % (tag, ip)] = np.array([len(v) for v in sel])
 
 
 def gen_misc(ep, out):

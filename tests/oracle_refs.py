@@ -98,6 +98,89 @@ def ep_reference(model):
     return compute_ep_reference(model)
 
 
+# ---- second cache: oracle posteriors used by the mix_pred / fit.py result tests -----------------------
+PATH2 = os.path.join(HERE, 'golden', 'nuts_ref2.npz')
+_cache2 = None
+PARAM_STATS_CASES = [('m1b', 1, 300, 4), ('m4b', 3, 240, 3), ('m2b', 2, 300, 3)]
+
+
+def _cached2(key, fn):
+    """dict of arrays under `key`: from tests/golden/nuts_ref2.npz, else computed (slow, on the calling host)"""
+    global _cache2
+    if _cache2 is None:
+        _cache2 = dict(np.load(PATH2)) if os.path.exists(PATH2) else {}
+    pre = key + '/'
+    hit = {k[len(pre):]: v for k, v in _cache2.items() if k.startswith(pre)}
+    return hit if hit else fn()
+
+
+def _transformed(model, q, d, J, D):
+    """alpha, beta of the Stan programs from draws q = [phi | eta | etb] (m1b.stan:30-36 ...), as one matrix"""
+    four = model in ('m4b', 'm5b')
+    ia, ib = (1, 2 + D) if four else (0, 1)
+    alpha = q[:, d:d + J] * np.exp(q[:, [ia]]) + (q[:, [0]] if four else 0.0)
+    if model == 'm1b':
+        return alpha
+    if model == 'm2b':
+        return np.concatenate([alpha, q[:, d + J:d + J + D] * np.exp(q[:, [ib]])], axis=1)
+    etb = q[:, d + J:].reshape(-1, J, D)
+    beta = etb * np.exp(q[:, None, ib:ib + D]) + (q[:, None, 2:2 + D] if four else 0.0)
+    return np.concatenate([alpha, beta.reshape(len(q), -1)], axis=1)
+
+
+def compute_param_stats_ref(model, J, n, D):
+    site = synth.make_site(model, n, D, J, seed=23)
+    td = dens.TiltedDensity(model, site['X'], site['y'], site['mu'], site['Omega'], j_ind=site['j_ind'], J=J)
+    q = nuts.sample(lambda v: tuple(w[0] for w in td.lp_grad(v[None])), td.p, chains=8, n_iter=1500, seed=5)['draws']
+    T = _transformed(model, q, site['d'], J, D)
+    return dict(mean=T.mean(axis=0), sd=T.std(axis=0))
+
+
+def param_stats_ref(model, J, n, D):
+    return _cached2('pstats_%s_%d_%d_%d' % (model, J, n, D), lambda: compute_param_stats_ref(model, J, n, D))
+
+
+def _fit_problem(model, J, D, npg, seed_data=100):
+    import importlib
+    exp = os.path.join(os.path.dirname(HERE), 'ep-stan_b200', 'experiment')
+    if exp not in sys.path:
+        sys.path.insert(0, exp)
+    mdl = importlib.import_module('models.' + model).model(J, D, npg)
+    data = mdl.simulate_data(Sigma_x='rand', rng=seed_data)
+    _, _, Q0, r0 = mdl.get_prior()
+    return data, Q0, r0
+
+
+def compute_fit_posterior(model, J, D, npg, chains=8, n_iter=1500, seed=3):
+    """full-data posterior of the fit.py problem (simulate_data seed 100) by the oracle NUTS:
+    moments of phi and of alpha"""
+    data, Q0, r0 = _fit_problem(model, J, D, npg)
+    td = dens.TiltedDensity(model, data.X, data.y, np.linalg.solve(Q0, r0), Q0, j_ind=data.j_ind, J=J)
+    q = nuts.sample(lambda v: tuple(w[0] for w in td.lp_grad(v[None])), td.p, chains=chains, n_iter=n_iter, seed=seed)['draws']
+    d = td.d
+    four = model in ('m4b', 'm5b')
+    alpha = q[:, d:d + J] * np.exp(q[:, [1 if four else 0]]) + (q[:, [0]] if four else 0.0)
+    return dict(phi_m=q[:, :d].mean(axis=0), phi_S=np.cov(q[:, :d].T), alpha_m=alpha.mean(axis=0), alpha_sd=alpha.std(axis=0))
+
+
+def fit_posterior(model, J, D, npg):
+    return _cached2('fitpost_%s_%d_%d_%d' % (model, J, D, npg), lambda: compute_fit_posterior(model, J, D, npg))
+
+
+def main2():
+    out = {}
+    for case in PARAM_STATS_CASES:
+        for k, v in compute_param_stats_ref(*case).items():
+            out['pstats_%s_%d_%d_%d/' % case + k] = v
+        print('pstats', case)
+    for case in (('m1b', 6, 2, 40), ('m1b', 8, 3, 40), ('m4b', 8, 3, 40)):
+        for k, v in compute_fit_posterior(*case).items():
+            out['fitpost_%s_%d_%d_%d/' % case + k] = v
+        print('fitpost', case)
+    np.savez_compressed(PATH2, **out)
+    print('wrote', PATH2, len(out), 'arrays')
+
+
 def main():
     out = {}
     for case in SAMPLER_CASES:
@@ -115,4 +198,7 @@ def main():
 
 
 if __name__ == '__main__':
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == '2':
+        main2()
+    else:
+        main()

@@ -244,23 +244,11 @@ def test_param_stats_for_mix_pred(model, J, n, D):
     assert np.max(np.abs(mean[0, :d] - dr.mean(axis=1))) < 1e-5 * max(1.0, np.max(np.abs(dr)))
     ssd_ref = ((dr - dr.mean(axis=1, keepdims=True)) ** 2).sum(axis=1)
     assert np.max(np.abs(ssd[0, :d] - ssd_ref) / ssd_ref) < 2e-3        # (fp32 running sums)
-    # alpha, beta: oracle NUTS on the same site, transformed as in the Stan programs
-    td = dens.TiltedDensity(model, site['X'], site['y'], site['mu'], site['Omega'], j_ind=site['j_ind'], J=J)
-    res = nuts.sample(lambda q: tuple(v[0] for v in td.lp_grad(q[None])), td.p, chains=8, n_iter=1500, seed=5)
-    q = res['draws']
-    four = model in ('m4b', 'm5b')
-    ia, ib = (1, 2 + D) if four else (0, 1)
-    alpha = q[:, d:d + J] * np.exp(q[:, [ia]]) + (q[:, [0]] if four else 0.0)
-    if model == 'm1b':
-        T = alpha
-    elif model == 'm2b':
-        T = np.concatenate([alpha, q[:, d + J:d + J + D] * np.exp(q[:, [ib]])], axis=1)
-    else:
-        etb = q[:, d + J:].reshape(-1, J, D)
-        beta = etb * np.exp(q[:, None, ib:ib + D]) + (q[:, None, 2:2 + D] if four else 0.0)
-        T = np.concatenate([alpha, beta.reshape(len(q), -1)], axis=1)
-    assert T.shape[1] == p - d
-    om, osd = T.mean(axis=0), T.std(axis=0)
+    # alpha, beta: oracle NUTS (8 x 1500) on the same site, transformed as in the Stan programs
+    # (cached: tests/oracle_refs.py, tests/golden/nuts_ref2.npz)
+    ref = oracle_refs.param_stats_ref(model, J, n, D)
+    om, osd = ref['mean'], ref['sd']
+    assert om.shape[0] == p - d
     gm = mean[0, d:p]
     gsd = np.sqrt(ssd[0, d:p] / (ntot - 1))
     mcse = osd * np.sqrt(1.0 / 400 + 1.0 / 400)                        # ~400 effective draws on either side
