@@ -69,17 +69,18 @@ def simulate_problem(model, K, n_k, D, seed=100):
 
 def synth_site(model, k, n_k, D, seed=100):
     """Cheap per-site generator for shapes whose full simulation does not fit the host
-    (config 5: 51 M rows x 199 inputs): standardised correlated inputs, group intercept/slopes."""
-    rng = np.random.RandomState([seed, k])
+    (config 5: 51 M rows x 199 inputs): standardised correlated inputs, group intercept/slopes.
+    (float32 normals from a counter-free SFC64 stream per site: 40 M normals per config-5 site)"""
+    rng = np.random.Generator(np.random.SFC64([seed, k]))
     g = np.random.RandomState(seed)                       # shared truth
     beta = g.standard_normal(D) * (0.5 if model != 'm1b' else 1.0) / np.sqrt(D / 4.0)
     sigma_b = np.exp(0.3 * g.standard_normal(D) - 1.0)
     alpha = rng.standard_normal() * 1.0
     bk = beta + (rng.standard_normal(D) * sigma_b if model != 'm1b' else 0.0)
-    X = rng.standard_normal((n_k, D))
-    X += 0.3 * rng.standard_normal((n_k, 1))              # common factor -> correlated inputs
-    f = alpha + X @ bk
-    y = (rng.uniform(size=n_k) < 1.0 / (1.0 + np.exp(-f))).astype(np.int64)
+    X = rng.standard_normal((n_k, D), dtype=np.float32)
+    X += 0.3 * rng.standard_normal((n_k, 1), dtype=np.float32)   # common factor -> correlated inputs
+    f = alpha + X @ bk.astype(np.float32)
+    y = (rng.random(n_k) < 1.0 / (1.0 + np.exp(-f.astype(np.float64)))).astype(np.int64)
     return X, y
 
 
@@ -94,8 +95,17 @@ def build_problem(model, K, n_k, D, k_begin, k_end, data='synth'):
         return simulate_problem(model, K, n_k, D)
     X = np.zeros((K * n_k, D))
     y = np.zeros(K * n_k, dtype=np.int64)
-    for k in range(k_begin, k_end):
+
+    def fill(k):
         X[k * n_k:(k + 1) * n_k], y[k * n_k:(k + 1) * n_k] = synth_site(model, k, n_k, D)
+
+    if (k_end - k_begin) * n_k * D > 1 << 26:             # large: the generator releases the GIL
+        import concurrent.futures
+        with concurrent.futures.ThreadPoolExecutor(max_workers=min(32, os.cpu_count() or 1)) as ex:
+            list(ex.map(fill, range(k_begin, k_end)))
+    else:
+        for k in range(k_begin, k_end):
+            fill(k)
     prior = {'Q': np.eye(d) / 1.5 ** 2, 'r': np.zeros(d)}
     return X, y, prior
 
@@ -454,6 +464,19 @@ def run_ours(args, model, K, n_k, D, chains, siter):
     kl_step = [kl_mvn(hist['m'][i], hist['S'][i], hist['m'][i - 1], hist['S'][i - 1]) for i in range(1, len(hist['m']))]
     rh = np.array(hist['mrhat'])
     x_bytes = n_loc * n_k * ((D + 3) * 4 + 64 * 2)
+    # A site whose bf16 design matrix exceeds what stays on chip / in L2 next to the other sites' (config 5: 83 MB per
+    # site) is streamed from HBM once per gradient evaluation of the site's chains: the sampler is HBM-bound there.
+    # Algorithmic bytes per evaluation of all chains: n_k * (2 D + 4) (bf16 X once + fp32 y once);
+    # evaluations = leapfrogs / chains (the chains of a site advance in lock-step).
+    hbm_roofline = None
+    site_bytes = n_k * (2.0 * D + 4.0)
+    if site_bytes * min(n_loc, 148) > 126e6 * 2:
+        gbs = (n_leap / chains / max(world, 1)) * site_bytes / max(samp_s, 1e-9) / 1e9
+        hbm_roofline = {'bound': 'hbm', 'achieved': gbs, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': gbs / hbm_peak,
+                        'traffic': load_traffic(args.workload, world), 'kernel': 'k_nuts<32,2> (wide tcgen05 pass)',
+                        'peak_source': peak_src + ' HBM copy bandwidth',
+                        'tensor': {'achieved': tf_achieved, 'peak': tf_peak, 'unit': 'TFLOP/s',
+                                   'frac': tf_achieved / tf_peak}}
     line = {
         'metric': 'EP iterations/sec (K sites, all draws)', 'value': its, 'unit': 'it/s',
         'n_gpus': world, 'steps': done, 'warmup': args.warmup, 'ms_per_step': ms_wall / max(done, 1),
@@ -482,7 +505,7 @@ def run_ours(args, model, K, n_k, D, chains, siter):
                 'steps': done2, 'ms_per_step': ms_wall2 / max(done2, 1)},
         'gpu_launches': launches,
         'clocks': clk,
-        'roofline': {'bound': 'tensor', 'achieved': tf_achieved, 'peak': tf_peak, 'unit': 'TFLOP/s',
+        'roofline': hbm_roofline if hbm_roofline else {'bound': 'tensor', 'achieved': tf_achieved, 'peak': tf_peak, 'unit': 'TFLOP/s',
                      'frac': tf_achieved / tf_peak, 'traffic': load_traffic(args.workload, world), 'kernel': 'k_nuts',
                      'peak_source': peak_src + ' bf16 sustained; contractions on tcgen05 (bf16 in, fp32 accumulate)',
                      # supplementary view: every gradient evaluation of a site's chains streams the site's bf16

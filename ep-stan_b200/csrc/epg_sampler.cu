@@ -48,14 +48,16 @@ struct epg_site_data {
     int K = 0;
     int64_t N = 0;
     float* X = nullptr;                 // [N][S]
-    __nv_bfloat16* Xb = nullptr;        // [N][64] bf16 copy for the tensor-core pass (column D = 1)
-    float* xmean = nullptr;             // [K][64] per-site column means the bf16 copy is centred on (0 beyond column D-1)
+    __nv_bfloat16* Xb = nullptr;        // [N][xb_pitch] bf16 copy for the tensor-core passes (column D = 1)
+    int nkc = 1, xb_pitch = 64;         // 64-column sub-tiles per tile; row pitch: 64 (D+1 <= 64) or D+1 rounded up to 16
+    float* gout_w = nullptr;            // wide pass scratch [K][2][32][256]
+    float* xmean = nullptr;             // [K][64 nkc] per-site column means the bf16 copy is centred on (0 beyond column D-1)
     int* order = nullptr;               // [K] launch order of the sites: most expensive (gradient evaluations of the
     std::vector<double> h_cost;         //     previous run, h_cost) first, so that stragglers do not start last
     unsigned char* reinit = nullptr;    // [K] 1: the next init_prev run starts this site's chains at random (epg_reinit_sites)
     std::vector<unsigned char> h_reinit;
-    CUtensorMap tmap;                   // TMA descriptor of Xb: box 64 x 128 rows, 128-byte swizzle
-    bool tc_ok = false;                 // tensor-core pass usable (single group, D+1 <= 64)
+    CUtensorMap tmap;                   // TMA descriptor of Xb: box 64 columns x 128 rows, 128-byte swizzle
+    bool tc_ok = false;                 // tensor-core passes usable (single group, D+1 <= 256)
     int use_tc = 1;                     // option (epg_set_option "use_tc")
     double* tstats = nullptr;           // [K][2][P] per-site mean and sum of squared deviations of the transformed
     size_t tstats_bytes = 0;            //     parameters over the last run's draws (option "param_stats", Master.mix_pred)
@@ -87,7 +89,7 @@ struct epg_site_data {
 void epg_sites_free(epg_ctx* c) {
     epg_site_data* s = c->sites;
     if (!s) return;
-    cudaFree(s->xmean); cudaFree(s->order); cudaFree(s->reinit); cudaFree(s->tstats);
+    cudaFree(s->xmean); cudaFree(s->gout_w); cudaFree(s->order); cudaFree(s->reinit); cudaFree(s->tstats);
     cudaFree(s->X); cudaFree(s->Xb); cudaFree(s->y); cudaFree(s->row0); cudaFree(s->grp_ptr); cudaFree(s->grp_rows);
     cudaFree(s->chain_mem); cudaFree(s->last_q); cudaFree(s->omega); cudaFree(s->out); cudaFree(s->ld_buf);
     delete s;
@@ -118,16 +120,17 @@ __global__ void k_convert_x(const double* __restrict__ src, float* __restrict__ 
 // within-site variation.  The means re-enter exactly: f = (alpha + c'beta) + (x - c)'beta and
 // G_col = sum_n e_n (x - c)_col + c_col sum_n e_n  (coefficient build / chain rule of likelihood_pass_tc).
 __global__ void k_convert_xb(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t rows, int S, int D,
-                             const float* __restrict__ xmean, const int64_t* __restrict__ row0, int K) {
+                             const float* __restrict__ xmean, const int64_t* __restrict__ row0, int K, int pitch,
+                             int xm_stride) {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= rows * 64) return;
-    const int64_t r = idx >> 6;
-    const int c = (int)(idx & 63);
+    if (idx >= rows * pitch) return;
+    const int64_t r = idx / pitch;
+    const int c = (int)(idx - r * pitch);
     float v = c < S ? src[r * S + c] : 0.0f;
     if (c < D) {
         int lo = 0, hi = K;                       // site of row r: row0[lo] <= r < row0[lo + 1]
         while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (row0[mid] <= r) lo = mid; else hi = mid; }
-        v -= xmean[(size_t)lo * 64 + c];
+        v -= xmean[(size_t)lo * xm_stride + c];
     }
     dst[idx] = __float2bfloat16(v);
 }
@@ -238,7 +241,9 @@ struct SamplerArgs {
     int k0;
     // shared-memory plan
     int R, resident, slices, NC, combos;
-    int use_tc, tc_nst, pp, hot_nvec, hot_levels, omega_smem;     // tc_nst: X/E stages of the tensor-core pass     // hot_levels: tree-stack levels kept in shared memory
+    float* gout_w;                     // wide tensor-core pass: [K][2][32][256] likelihood-gradient halves (global scratch)
+    int nkc, xm_stride;                // 64-column sub-tiles per tile; stride of xmean (64 * nkc)
+    int use_tc, tc_nst, pp, hot_nvec, hot_levels, omega_smem;     // use_tc: 0 SIMT, 1 tensor-core pass, 2 wide tensor-core pass; tc_nst: X/E stages of the tensor-core pass     // hot_levels: tree-stack levels kept in shared memory
     size_t off_E, off_B, off_G, off_gphi, off_cavc, off_lp, off_cs, off_hot, off_omega, smem_total;
     size_t site_stride;                // ping-pong kernel: distance between the two per-site blocks
 };
@@ -277,6 +282,7 @@ __device__ __forceinline__ float logit_terms(float f, float yv, float& e) {
 }
 
 #include "epg_lik_tc.cuh"
+#include "epg_lik_tcw.cuh"
 
 // shared-memory load through the shared window (ld.shared).  The pointers the sampler works with are generic
 // (a vector lives in shared OR global memory depending on the launch plan), and generic loads take the L1TEX
@@ -669,6 +675,109 @@ __device__ void likelihood_pass_tc(const SamplerArgs& a, unsigned char* smem, un
 #ifdef EPG_TC_PROFILE
     if (threadIdx.x == 0) { PROF2_ADD(2, q0, q1); PROF2_ADD(3, q1, q2); PROF2_ADD(4, q2, q3); PROF2_ADD(5, q3, q4); PROF2_ADD(6, 0, 1); }
 #endif
+}
+
+// ---------------------------------------------------------------------------
+// Wide tensor-core variant (single-group sites, D+1 <= 256, <= 32 chains; config 5): see epg_lik_tcw.cuh.
+// Same outputs as likelihood_pass.  The chain vectors may live in global memory here (generic pointers).
+// ---------------------------------------------------------------------------
+__device__ void likelihood_pass_tcw(const SamplerArgs& a, unsigned char* smem, unsigned char* tcb, uint32_t tmem_base,
+                                    const CUtensorMap* tmap, tcw::State& st, int k_local, int nchains,
+                                    int64_t row_begin, int n_rows, double* lp_out, const float* om, const float* muf) {
+    const int tid = threadIdx.x;
+    const bool worker = tid < NTHR;
+    const int D = a.D, d = a.d, model = a.model;
+    double* lpw = reinterpret_cast<double*>(smem + a.off_lp);       // [NWARP][32]
+    const bool four = model_four(model);
+    const int ia = four ? 1 : 0;
+    const int ib = four ? 2 + D : 1;
+    const int ncol = a.nkc * tc::KW;
+    const float* xm = a.xmean + (size_t)k_local * a.xm_stride;
+    float* gout = a.gout_w + (size_t)k_local * 2 * tcw::NCH * tcw::KWT;
+    if (worker) {
+        // coefficient operand B = B_hi + B_lo (bf16 each); one warp per chain, lane l builds columns l + 32 h.
+        // Centred design matrix: the intercept coefficient (column D) carries  alpha + sum_col mean_col * beta_col.
+        const int lane = tid & 31;
+        for (int c = tid >> 5; c < nchains; c += NWARP) {
+            const float* q = cvec(a, SiteView{smem, k_local}, c, V_Q);
+            float v[tcw::KWT / 32];
+            float mterm = 0.0f;
+#pragma unroll
+            for (int h = 0; h < tcw::KWT / 32; ++h) {
+                const int col = lane + 32 * h;
+                float b = 0.0f;
+                if (col < D) {
+                    if (model == EPG_M1B) b = q[1 + col];
+                    else if (model == EPG_M2B) b = q[d + 1 + col] * __expf(q[ib]);
+                    else b = q[d + 1 + col] * __expf(q[ib + col]) + (four ? q[2 + col] : 0.0f);
+                    mterm = fmaf(xm[col], b, mterm);
+                }
+                v[h] = b;
+            }
+            mterm = warp_sum(mterm);
+#pragma unroll
+            for (int h = 0; h < tcw::KWT / 32; ++h) {
+                const int col = lane + 32 * h;
+                if (col >= ncol) continue;
+                if (col == D) v[h] = q[d] * __expf(q[ia]) + (four ? q[0] : 0.0f) + mterm;
+                const __nv_bfloat16 hi = __float2bfloat16(v[h]);
+                const __nv_bfloat16 lo = __float2bfloat16(v[h] - __bfloat162float(hi));
+                *reinterpret_cast<__nv_bfloat16*>(tcb + tcw::Smem::BM + tcw::b_off(c, col)) = hi;
+                *reinterpret_cast<__nv_bfloat16*>(tcb + tcw::Smem::BM + tcw::b_off(tcw::NCH + c, col)) = lo;
+            }
+        }
+        tc::fence_proxy_async();
+    }
+    lik_group_sync();
+    const int ksteps = (D + 1 + 15) / 16;
+    auto prologue = [&]() { cavity_term(a, smem, om, muf, k_local, nchains, NTHR); };
+    tcw::pass(tcb, tmem_base, tmap, st, row_begin, n_rows, a.nkc, ksteps, a.y, lpw, gout, prologue);
+    lik_group_sync();
+    if (worker) {
+        // chain rule (single group: every slot of the likelihood gradient gets exactly one term)
+        const float* g0 = gout;
+        const float* g1 = gout + (size_t)tcw::NCH * tcw::KWT;
+        for (int e = tid; e < nchains * ncol; e += NTHR) {
+            const int c = e / ncol, col = e - c * ncol;
+            if (col > D) continue;
+            const float se = g0[c * tcw::KWT + D] + g1[c * tcw::KWT + D];            // sum_n e_n
+            float gsum = g0[c * tcw::KWT + col] + g1[c * tcw::KWT + col];
+            if (col < D) gsum = fmaf(xm[col], se, gsum);                             // centred inputs
+            const float* q = cvec(a, SiteView{smem, k_local}, c, V_Q);
+            float* gl = cvec(a, SiteView{smem, k_local}, c, V_GL);
+            if (col == D) {
+                const float sa = __expf(q[ia]);
+                gl[d] = sa * gsum;
+                gl[ia] = sa * q[d] * gsum;
+                if (four) gl[0] = gsum;
+            } else if (model == EPG_M1B) {
+                gl[1 + col] = gsum;
+            } else if (model == EPG_M2B) {
+                gl[d + 1 + col] = __expf(q[ib]) * gsum;       // (log sigma_b: below, one thread per chain)
+            } else {
+                const float sb = __expf(q[ib + col]);
+                const float etb = q[d + 1 + col];
+                gl[d + 1 + col] = sb * gsum;
+                gl[ib + col] = sb * etb * gsum;
+                if (four) gl[2 + col] = gsum;
+            }
+        }
+        if (tid < nchains) {
+            double sum = 0.0;
+            for (int w = 0; w < NWARP; ++w) sum += lpw[w * tcw::NCH + tid];
+            lp_out[tid] = sum;
+            if (model == EPG_M2B) {
+                // d/d log sigma_b = sigma_b sum_i etb_i g_i, in a fixed order
+                const float* q = cvec(a, SiteView{smem, k_local}, tid, V_Q);
+                float acc = 0.0f;
+                const float se = g0[tid * tcw::KWT + D] + g1[tid * tcw::KWT + D];
+                for (int col = 0; col < D; ++col)
+                    acc = fmaf(q[d + 1 + col], fmaf(xm[col], se, g0[tid * tcw::KWT + col] + g1[tid * tcw::KWT + col]), acc);
+                cvec(a, SiteView{smem, k_local}, tid, V_GL)[ib] = __expf(q[ib]) * acc;
+            }
+        }
+    }
+    lik_group_sync();
 }
 
 // ---------------------------------------------------------------------------
@@ -1374,11 +1483,12 @@ __device__ void site_analytics(const SamplerArgs& a, const SiteView& sv, const C
 // ---------------------------------------------------------------------------
 // the persistent sampling kernel: one CTA per site
 // ---------------------------------------------------------------------------
-// USE_TC false: fp32 SIMT likelihood pass (NTHR threads); true: tensor-core pass (tc::NTHREADS threads)
-template <int CP, bool USE_TC>
-__global__ void __launch_bounds__(USE_TC ? tc::NTHREADS : NTHR, 1)
+// TCM 0: fp32 SIMT likelihood pass (NTHR threads); 1: tensor-core pass, 2: wide tensor-core pass (tc::NTHREADS threads)
+template <int CP, int TCM>
+__global__ void __launch_bounds__(TCM ? tc::NTHREADS : NTHR, 1)
 k_nuts(const SamplerArgs a, const __grid_constant__ CUtensorMap tmap) {
     extern __shared__ __align__(1024) unsigned char smem[];
+    constexpr bool USE_TC = TCM == 1, USE_TCW = TCM == 2;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int site_off = a.order ? a.order[blockIdx.x] : (int)blockIdx.x;    // most expensive sites first
     const int k_local = a.k0 + site_off;
@@ -1402,7 +1512,7 @@ k_nuts(const SamplerArgs a, const __grid_constant__ CUtensorMap tmap) {
     float* muf = om + d * d;
     if (worker) load_cavity(a, k_local, om, tid, NTHR);
     // resident design matrix
-    if (!USE_TC && a.resident) {
+    if (TCM == 0 && a.resident) {
         const float4* src = reinterpret_cast<const float4*>(a.X + (size_t)row_begin * S);
         float4* dst = reinterpret_cast<float4*>(smem);
         for (int e = tid; e < n_rows * (S >> 2); e += NTHR) dst[e] = src[e];
@@ -1411,9 +1521,14 @@ k_nuts(const SamplerArgs a, const __grid_constant__ CUtensorMap tmap) {
     unsigned char* tcb = smem + ((1024u - (tc::smem_u32(smem) & 1023u)) & 1023u);
     uint32_t tmem_base = 0;
     tc::State tcst;
+    tcw::State tcwst;
     if constexpr (USE_TC) {
         tcst.set_stages(a.tc_nst);
         tmem_base = tc::setup(tcb, a.tc_nst);
+    }
+    if constexpr (USE_TCW) {
+        tcwst.nst = (uint32_t)a.tc_nst;
+        tmem_base = tcw::setup(tcb);
     }
     if (worker) init_chains(a, sv, cs, warp, NWARP, lane);
     if (tid == 0) n_active = C;
@@ -1430,12 +1545,14 @@ k_nuts(const SamplerArgs a, const __grid_constant__ CUtensorMap tmap) {
         if (n_active <= 0) break;
         const long long tk1 = clock64();
         if constexpr (USE_TC) likelihood_pass_tc(a, smem, tcb, tmem_base, &tmap, tcst, k_local, C, row_begin, n_rows, lp_lik, om, muf);
+        else if constexpr (USE_TCW) likelihood_pass_tcw(a, smem, tcb, tmem_base, &tmap, tcwst, k_local, C, row_begin, n_rows, lp_lik, om, muf);
         else likelihood_pass<CP>(a, smem, k_local, k_local, C, J, row_begin, n_rows, grows, lp_lik, om, muf);
         clk_chain += tk1 - tk0;
         clk_lik += clock64() - tk1;
         ++n_ticks;
     }
     if constexpr (USE_TC) tc::teardown(tmem_base);
+    if constexpr (USE_TCW) tcw::teardown(tmem_base);
     __syncthreads();
     if (warp == 0) site_analytics(a, sv, cs, p, lane, (double)clk_chain, (double)clk_lik, (double)n_ticks);
 }
@@ -1576,9 +1693,13 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) k_logdensity(const SamplerArg
     unsigned char* tcb = smem + ((1024u - (tc::smem_u32(smem) & 1023u)) & 1023u);
     uint32_t tmem_base = 0;
     tc::State tcst;
-    if (a.use_tc) {
+    tcw::State tcwst;
+    if (a.use_tc == 1) {
         tcst.set_stages(a.tc_nst);
         tmem_base = tc::setup(tcb, a.tc_nst);
+    } else if (a.use_tc == 2) {
+        tcwst.nst = (uint32_t)a.tc_nst;
+        tmem_base = tcw::setup(tcb);
     }
     // the evaluation points were staged in the global copy of V_Q (k_set_q)
     if (worker && a.hot_nvec > V_Q)
@@ -1588,7 +1709,11 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) k_logdensity(const SamplerArg
         }
     __threadfence_block();
     __syncthreads();
-    if (a.use_tc) {
+    if (a.use_tc == 2) {
+        // (twice: exercises the pipeline state carried across ticks)
+        likelihood_pass_tcw(a, smem, tcb, tmem_base, &tmap, tcwst, k_local, nq, row_begin, n_rows, lp_lik, om, muf);
+        likelihood_pass_tcw(a, smem, tcb, tmem_base, &tmap, tcwst, k_local, nq, row_begin, n_rows, lp_lik, om, muf);
+    } else if (a.use_tc) {
         likelihood_pass_tc(a, smem, tcb, tmem_base, &tmap, tcst, k_local, nq, row_begin, n_rows, lp_lik, om, muf);
         // second evaluation: exercises the pipeline state carried across ticks
         likelihood_pass_tc(a, smem, tcb, tmem_base, &tmap, tcst, k_local, nq, row_begin, n_rows, lp_lik, om, muf);
@@ -1603,7 +1728,8 @@ __global__ void __launch_bounds__(tc::NTHREADS, 1) k_logdensity(const SamplerArg
         if (lane == 0) lp_out[c] = -V;
         for (int i = lane; i < p; i += 32) grad_out[(size_t)c * p + i] = -(double)g[i];
     }
-    if (a.use_tc) tc::teardown(tmem_base);
+    if (a.use_tc == 1) tc::teardown(tmem_base);
+    if (a.use_tc == 2) tcw::teardown(tmem_base);
 }
 
 __global__ void k_set_q(float* chain_mem, int chain0, int P, int p, int nq, const double* q) {
@@ -1640,6 +1766,24 @@ bool plan_smem(SamplerArgs& a, int CP, int64_t max_rows, int d, size_t budget = 
         }
         return o;
     };
+    if (a.use_tc == 2) {
+        // wide pass: [coefficients | barriers | 4 E buffers | nst X sub-tiles][cavity terms][lp][chain scalars][tail];
+        // ring as deep as fits, at most min(8, 4 nkc) stages (E-buffer reuse rule of epg_lik_tcw.cuh)
+        a.off_E = a.off_B = a.off_G = a.off_gphi = 0;
+        a.R = 0; a.resident = 0; a.slices = 1; a.NC = 1; a.combos = 1;
+        const size_t fixed = al16(sizeof(float) * (size_t)tcw::NCH * d) + al16(sizeof(double) * (size_t)NWARP * tcw::NCH) + sz_cs;
+        int nst = std::min(tcw::NST, 4 * a.nkc);
+        if (const char* e = getenv("EPGPU_NST")) nst = std::max(2, std::min(nst, atoi(e)));
+        while (nst >= 2 && al16(1024 + tcw::Smem::total(nst)) + fixed > budget) --nst;
+        if (nst < 2 || nst < a.nkc) return false;
+        a.tc_nst = nst;
+        size_t o = al16(1024 + tcw::Smem::total(nst));
+        a.off_cavc = o; o += al16(sizeof(float) * (size_t)tcw::NCH * d);
+        a.off_lp = o; o += al16(sizeof(double) * (size_t)NWARP * tcw::NCH);
+        a.off_cs = o; o += sz_cs;
+        a.smem_total = place_tail(o);
+        return true;
+    }
     if (a.use_tc) {
         if (a.tc_nst < tc::NF || a.tc_nst > tc::NST) a.tc_nst = tc::NST;
         size_t o = al16(1024 + tc::Smem::total(a.tc_nst));      // 1024: alignment slack for the swizzled tiles
@@ -1821,13 +1965,18 @@ int epg_upload_sites(epg_ctx* c, int model, int D, const int64_t* k_lim, const d
     }
     EPG_CHECK(c, cudaFree(stage));
     EPG_CHECK(c, cudaGetLastError());
-    // tensor-core path: bf16 copy [N][64] + TMA descriptor (single-group sites, D+1 <= 64)
+    // tensor-core paths: bf16 copy [N][pitch] + TMA descriptor (single-group sites, D+1 <= 256).  D+1 <= 64: one
+    // 64-column box per 128-row tile (pitch 64); wider: nkc boxes per tile, pitch = D+1 rounded up to 16 columns
+    // (32-byte sectors); the columns of the last box beyond the pitch are out of bounds (zero-filled by TMA)
     s->tc_ok = false;
     memset(&s->tmap, 0, sizeof(s->tmap));
-    if (s->Jmax == 1 && D + 1 <= tc::KW) {
-        EPG_CHECK(c, cudaMalloc((void**)&s->Xb, sizeof(__nv_bfloat16) * (size_t)N * tc::KW));
+    if (s->Jmax == 1 && D + 1 <= tcw::KWT) {
+        s->nkc = (D + 1 + tc::KW - 1) / tc::KW;
+        s->xb_pitch = s->nkc == 1 ? tc::KW : ((D + 1 + 15) / 16) * 16;
+        const int xm_stride = tc::KW * s->nkc;
+        EPG_CHECK(c, cudaMalloc((void**)&s->Xb, sizeof(__nv_bfloat16) * (size_t)N * s->xb_pitch));
         // per-site column means (fp64 on the host, stored as fp32) the bf16 copy is centred on
-        std::vector<float> xm((size_t)K * tc::KW, 0.0f);
+        std::vector<float> xm((size_t)K * xm_stride, 0.0f);
         {
             std::vector<double> acc(D);
             for (int k = 0; k < K; ++k) {
@@ -1837,13 +1986,14 @@ int epg_upload_sites(epg_ctx* c, int model, int D, const int64_t* k_lim, const d
                     const double* xr = X + (size_t)(base + r) * D;
                     for (int j = 0; j < D; ++j) acc[j] += xr[j];
                 }
-                for (int j = 0; j < D; ++j) xm[(size_t)k * tc::KW + j] = (float)(acc[j] / (double)(hi - lo));
+                for (int j = 0; j < D; ++j) xm[(size_t)k * xm_stride + j] = (float)(acc[j] / (double)(hi - lo));
             }
         }
         EPG_CHECK(c, cudaMalloc((void**)&s->xmean, sizeof(float) * xm.size()));
         EPG_CHECK(c, cudaMemcpyAsync(s->xmean, xm.data(), sizeof(float) * xm.size(), cudaMemcpyHostToDevice, c->stream));
-        const int64_t tot = N * tc::KW;
-        k_convert_xb<<<(unsigned)((tot + 255) / 256), 256, 0, c->stream>>>(s->X, s->Xb, N, S, D, s->xmean, s->row0, K);
+        const int64_t tot = N * s->xb_pitch;
+        k_convert_xb<<<(unsigned)((tot + 255) / 256), 256, 0, c->stream>>>(s->X, s->Xb, N, S, D, s->xmean, s->row0, K,
+                                                                        s->xb_pitch, xm_stride);
         c->launches++;
         EPG_CHECK(c, cudaStreamSynchronize(c->stream));
         typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -1853,8 +2003,8 @@ int epg_upload_sites(epg_ctx* c, int model, int D, const int64_t* k_lim, const d
         cudaDriverEntryPointQueryResult qres;
         EPG_CHECK(c, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
         if (fn && qres == cudaDriverEntryPointSuccess) {
-            const cuuint64_t gdim[2] = {(cuuint64_t)tc::KW, (cuuint64_t)N};
-            const cuuint64_t gstride[1] = {(cuuint64_t)tc::KW * 2};
+            const cuuint64_t gdim[2] = {(cuuint64_t)s->xb_pitch, (cuuint64_t)N};
+            const cuuint64_t gstride[1] = {(cuuint64_t)s->xb_pitch * 2};
             const cuuint32_t box[2] = {(cuuint32_t)tc::KW, (cuuint32_t)tc::TILE_M};
             const cuuint32_t estr[2] = {1, 1};
             const CUresult r = ((encode_fn)fn)(&s->tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, s->Xb, gdim, gstride, box, estr,
@@ -1862,6 +2012,7 @@ int epg_upload_sites(epg_ctx* c, int model, int D, const int64_t* k_lim, const d
                                                CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             s->tc_ok = (r == CUDA_SUCCESS);
         }
+        if (s->tc_ok) EPG_CHECK(c, cudaMalloc((void**)&s->gout_w, sizeof(float) * (size_t)K * 2 * tcw::NCH * tcw::KWT));
     }
     return 0;
 }
@@ -1928,7 +2079,13 @@ static int fill_args(epg_ctx* c, SamplerArgs& a, int C, int CP, int n_sites = 1,
         EPG_CHECK(c, epg_reserve((void**)&s->tstats, &s->tstats_bytes, sizeof(double) * (size_t)c->K * 2 * s->Pmax));
         a.tstats = s->tstats;
     }
-    a.use_tc = (s->tc_ok && s->use_tc && C <= tc::NCH) ? 1 : 0;
+    // tensor-core pass: 1 = D+1 <= 64 and <= 16 chains (chain vectors in shared memory), 2 = wide (D+1 <= 256, <= 32 chains)
+    a.use_tc = (s->tc_ok && s->use_tc) ? ((s->nkc == 1 && C <= tc::NCH) ? 1 : (C <= tcw::NCH ? 2 : 0)) : 0;
+    a.nkc = s->nkc; a.xm_stride = tc::KW * s->nkc; a.gout_w = s->gout_w;
+    if (a.use_tc == 2) {
+        if (!plan_smem(a, CP, s->max_rows, c->d)) { a.use_tc = 0; }
+        else return 0;
+    }
     // More sites than SMs: the ping-pong kernel (two sites per persistent CTA) if both per-site blocks fit.
     a.tc_nst = tc::NST;
     a.pp = 0;
@@ -1937,7 +2094,7 @@ static int fill_args(epg_ctx* c, SamplerArgs& a, int C, int CP, int n_sites = 1,
     // (the kernel doubles the number of sites streamed concurrently: it only pays while the bf16 design
     //  matrices of 2 x SMs sites stay resident in L2 -- measured: config 4, 640 KB per site, does not)
     const double resident_bytes = 2.0 * c->num_sms * (double)s->max_rows * tc::KW * 2.0;
-    const int pp = a.use_tc && s->Jmax == 1 && n_sites > 1 &&
+    const int pp = a.use_tc == 1 && s->Jmax == 1 && n_sites > 1 &&
                    (mode == 2 || (mode == 1 && n_sites > c->num_sms && resident_bytes <= 0.75 * c->l2_bytes));
     if (pp && plan_smem_pp(a, c->d)) return 0;
     a.pp = 0;
@@ -2037,9 +2194,10 @@ int epg_tilted_sample(epg_ctx* c, int k0, int k1, const uint32_t* seeds, const e
         if (const char* e = getenv("EPGPU_PP_GRID")) grid = std::max(1, std::min(atoi(e), k1 - k0));
         k_nuts_pp<<<grid, PP_THREADS, a.smem_total, c->stream>>>(a, s->tmap, k1 - k0, queue);
     }
-    else if (a.use_tc) LAUNCH_NUTS(32, true)
-    else if (CP == 4) LAUNCH_NUTS(4, false) else if (CP == 8) LAUNCH_NUTS(8, false)
-    else if (CP == 16) LAUNCH_NUTS(16, false) else LAUNCH_NUTS(32, false)
+    else if (a.use_tc == 2) LAUNCH_NUTS(32, 2)
+    else if (a.use_tc) LAUNCH_NUTS(32, 1)
+    else if (CP == 4) LAUNCH_NUTS(4, 0) else if (CP == 8) LAUNCH_NUTS(8, 0)
+    else if (CP == 16) LAUNCH_NUTS(16, 0) else LAUNCH_NUTS(32, 0)
     c->launches++;
     EPG_CHECK(c, cudaGetLastError());
     EPG_CHECK(c, cudaEventRecord(e1, c->stream));
@@ -2142,7 +2300,7 @@ int epg_logdensity(epg_ctx* c, int k, int nq, const double* q, double* lp_out, d
     if (!c->sites || k < 0 || k >= c->K || nq < 1) return epg_fail_msg(c, "epg_logdensity: bad args");
     epg_site_data* s = c->sites;
     const int p = s->h_p[k];
-    const int C = (s->tc_ok && s->use_tc) ? tc::NCH : 32, CP = 32;
+    const int C = (s->tc_ok && s->use_tc && s->nkc == 1) ? tc::NCH : 32, CP = 32;
     SamplerArgs a;
     memset(&a, 0, sizeof(a));
     if (int rc = fill_args(c, a, C, CP)) return rc;

@@ -81,6 +81,30 @@ def test_logdensity_parity_tensor_core(model, n, D):
     ctx.close()
 
 
+@pytest.mark.parametrize('model,n,D', [('m1b', 300, 64), ('m1b', 1300, 127), ('m3b', 700, 130),
+                                       ('m1b', 2100, 199), ('m3b', 900, 199), ('m4b', 500, 100),
+                                       ('m2b', 640, 90), ('m1b', 37, 255)])
+def test_logdensity_parity_wide_tensor_core(model, n, D):
+    """Wide tcgen05/TMA pass (csrc/epg_lik_tcw.cuh; config 5: D+1 up to 256 in 64-column sub-tiles whose GEMM1
+    partial products accumulate in TMEM, 32 chains): same check as above, against the fp64 oracle on the
+    stored (centred, bf16) inputs.  Shapes cover 2, 3 and 4 sub-tiles, a last sub-tile with a single
+    K-step (D+1 = 65), the full 256 columns and ragged last row tiles."""
+    sites = [synth.make_site(model, n, D, 1, seed=61), synth.make_site(model, n + 77, D, 1, seed=62)]
+    for s in sites:                                  # (keep the cavity term moderate at d = 200)
+        s['Omega'] = s['Omega'] / max(1.0, np.abs(s['Omega']).max()) + np.eye(s['d'])
+    ctx = make_ctx(model, sites, use_tc=1)
+    rng = np.random.RandomState(5)
+    for k, site in enumerate(sites):
+        site_q = dict(site, X=synth.tc_stored_X(site['X']))
+        td = synth.oracle_density(model, site_q)
+        q = (0.4 / np.sqrt(max(D, 16) / 16.0)) * rng.standard_normal((40, td.p))     # > 32: exercises batching
+        lp, grad = ctx.logdensity(k, q)
+        olp, ograd = td.lp_grad(q)
+        assert np.max(np.abs(lp - olp) / np.maximum(1.0, np.abs(olp))) < 5e-5
+        assert np.max(np.abs(grad - ograd)) < 6e-3 * max(1.0, np.max(np.abs(ograd)))
+    ctx.close()
+
+
 def test_tensor_core_pass_keeps_shifted_inputs():
     """Inputs like 35.5 +- 0.02 (the simulators shift the inputs of groups with extreme intercepts,
     common.py:132-317): plain bf16 storage (8 significant bits) would erase the within-site variation;
@@ -128,7 +152,9 @@ def _moment_check(draws_gpu, per_chain_gpu, ref):
 
 @pytest.mark.parametrize('model,J,n,D,C', [('m1b', 1, 300, 4, 8), ('m3b', 1, 400, 3, 8),
                                            ('m4b', 2, 300, 3, 4), ('m1b', 5, 250, 6, 16),
-                                           ('m2b', 3, 300, 4, 8), ('m5b', 1, 300, 3, 8)])
+                                           ('m2b', 3, 300, 4, 8), ('m5b', 1, 300, 3, 8),
+                                           # wide tensor-core pass: > 16 chains (one sub-tile), D+1 > 64 (two)
+                                           ('m1b', 1, 300, 4, 24), ('m1b', 1, 600, 70, 32)])
 def test_sampler_vs_oracle_nuts(model, J, n, D, C):
     site = synth.make_site(model, n, D, J, seed=21)
     NS = 6
