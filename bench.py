@@ -354,6 +354,8 @@ def run_ours(args, model, K, n_k, D, chains, siter):
         kw['rhat_max'] = args.rhat_max
     if args.no_adapt_prev:
         kw['adapt_prev'] = False
+    if args.max_treedepth:
+        kw['control'] = {'max_treedepth': args.max_treedepth}
     m = method.Master('experiment/models/%s_sg' % model, X, y, site_sizes=np.full(K, n_k), prior=prior,
                       chains=chains, iter=siter, **kw)
     n_sample = min(K, max(os.cpu_count() or 1, 2))
@@ -491,6 +493,7 @@ def run_ours(args, model, K, n_k, D, chains, siter):
                                'auto1': 'automatic selection (df_select=snr), no cap',
                                'schedule': 'fit.py default_df0'}[args.damp],
                    'rhat_max': args.rhat_max if args.rhat_max > 0 else None,
+                   'max_treedepth': args.max_treedepth or 10,
                    'warmup_start': ("Stan defaults (unit metric, step size 1) every EP iteration" if args.no_adapt_prev else
                                     "init_prev carries the last draw AND the adapted metric / step size of each chain "
                                     "(adapt_prev=True, an extension; --no-adapt-prev for Stan's defaults)"),
@@ -555,6 +558,8 @@ def main():
     ap.add_argument('--no-adapt-prev', action='store_true',
                     help="Stan's unit metric / step size 1 at the start of every warm-up (the reference's behaviour)")
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--max-treedepth', type=int, default=None,
+                    help="NUTS control (Stan's default 10); bounds the step time of --workload cfg5, stated in config")
     args = ap.parse_args()
     model, K, n_k, D, chains, siter = WORKLOADS[args.workload]
     K = args.sites or K

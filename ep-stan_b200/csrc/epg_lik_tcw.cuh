@@ -6,7 +6,7 @@
 //   design matrix: bf16 [N][pitch], pitch = (D+1 rounded up to 16) columns, centred per site, column D = 1;
 //   a 128-row tile is nkc = ceil((D+1)/64) sub-tiles of 64 columns, each a TMA box [128 rows x 128 B]
 //   (128-byte swizzle; the columns beyond `pitch` of the last box are out of bounds = zero-filled without
-//   HBM traffic) in its own stage of a ring of up to 8 x 16 kB stages.
+//   HBM traffic) in its own stage of a ring of up to 10 x 16 kB stages (9 fit on config 5).
 //     GEMM1  F[128 x 64] = sum_j X_sub_j[128 x 64] . [B_hi | B_lo]_j'[64 x 64]   (K-chunked over the sub-tiles,
 //              accumulated in one of 4 TMEM buffers; M=128, N=64 = 32 chains hi | 32 chains lo, K=16 per MMA)
 //     epilogue (8 warps = two groups on alternate tiles, one row per thread): tcgen05.ld F_hi, F_lo ->
@@ -34,7 +34,7 @@ constexpr int NCH = 32;              // chains (N of GEMM2, half the N of GEMM1)
 constexpr int NB1 = 2 * NCH;         // GEMM1 N: columns [0,32) hi parts, [32,64) lo parts of the coefficients
 constexpr int NKC = 4;               // max sub-tiles (64-column chunks) per tile
 constexpr int KWT = NKC * KW;        // 256 padded coefficient columns
-constexpr int NST = 8;               // max ring stages (one sub-tile each)
+constexpr int NST = 10;              // max ring stages (one sub-tile each)
 constexpr int NF = 4;                // F accumulator buffers in TMEM == E buffers in smem
 constexpr int B_BYTES = NB1 * KWT * 2;               // 32768
 constexpr int E_BYTES = NCH * TILE_M * 2;            // 8192

@@ -242,6 +242,7 @@ struct SamplerArgs {
     // shared-memory plan
     int R, resident, slices, NC, combos;
     float* gout_w;                     // wide tensor-core pass: [K][2][32][256] likelihood-gradient halves (global scratch)
+    float* cavc_g;                     // wide pass: cavity terms [K][32][d] in global memory (shared memory goes to the TMA ring)
     int nkc, xm_stride;                // 64-column sub-tiles per tile; stride of xmean (64 * nkc)
     int use_tc, tc_nst, pp, hot_nvec, hot_levels, omega_smem;     // use_tc: 0 SIMT, 1 tensor-core pass, 2 wide tensor-core pass; tc_nst: X/E stages of the tensor-core pass     // hot_levels: tree-stack levels kept in shared memory
     size_t off_E, off_B, off_G, off_gphi, off_cavc, off_lp, off_cs, off_hot, off_omega, smem_total;
@@ -298,7 +299,7 @@ __device__ __forceinline__ float lds_ro(uint32_t saddr) {
 // dot product per thread) into shared memory; consumed by finish_gradient.
 __device__ __forceinline__ void cavity_term(const SamplerArgs& a, unsigned char* smem, const float* om, const float* muf,
                                             int k_local, int nchains, int nthr_workers) {
-    float* cavc = reinterpret_cast<float*>(smem + a.off_cavc);
+    float* cavc = a.cavc_g ? a.cavc_g + (size_t)k_local * tcw::NCH * a.d : reinterpret_cast<float*>(smem + a.off_cavc);
     const int d = a.d;
     const bool in_smem = a.omega_smem && a.hot_nvec > V_Q;
     for (int e = threadIdx.x; e < nchains * d; e += nthr_workers) {
@@ -833,7 +834,8 @@ __device__ __forceinline__ ChainCtxT<ALLHOT> make_chain_ctx(const SamplerArgs& a
     const int cg = sv.k * a.C + c_local;
     float* hot = cvec(a, sv, c_local, 0);    // slot 0 of the chain's shared block (when hot_nvec > 0)
     float* cold = a.chain_mem + (size_t)cg * NVEC * a.P;
-    const float* cavc = reinterpret_cast<const float*>(sv.sm + a.off_cavc) + (size_t)c_local * d;
+    const float* cavc = (a.cavc_g ? a.cavc_g + (size_t)sv.k * tcw::NCH * d
+                                  : reinterpret_cast<const float*>(sv.sm + a.off_cavc)) + (size_t)c_local * d;
     const uint32_t per_chain = (uint32_t)(a.hot_nvec + 4 * a.hot_levels);
     const uint32_t hot_off = sv.off + (uint32_t)a.off_hot + (uint32_t)c_local * per_chain * (uint32_t)a.P * 4u;
     const uint32_t cavc_off = sv.off + (uint32_t)a.off_cavc + (uint32_t)(c_local * d) * 4u;
@@ -1767,18 +1769,20 @@ bool plan_smem(SamplerArgs& a, int CP, int64_t max_rows, int d, size_t budget = 
         return o;
     };
     if (a.use_tc == 2) {
-        // wide pass: [coefficients | barriers | 4 E buffers | nst X sub-tiles][cavity terms][lp][chain scalars][tail];
-        // ring as deep as fits, at most min(8, 4 nkc) stages (E-buffer reuse rule of epg_lik_tcw.cuh)
-        a.off_E = a.off_B = a.off_G = a.off_gphi = 0;
+        // wide pass: [coefficients | barriers | 4 E buffers | nst X sub-tiles][lp][chain scalars][tail]; the cavity
+        // terms live in global memory (cavc_g).  The ring is as deep as fits, at most min(NST, 4 nkc) stages (E-buffer
+        // reuse rule of epg_lik_tcw.cuh): the pass is HBM-bound and lives on the TMA bytes in flight -- measured on
+        // config 5: 7 stages 3.6k cycles per 64 kB tile (the last sub-tile of the next tile is issued only when the
+        // first GEMM2 of this one retires), against 2.9k at the HBM roofline
+        a.off_E = a.off_B = a.off_G = a.off_gphi = a.off_cavc = 0;
         a.R = 0; a.resident = 0; a.slices = 1; a.NC = 1; a.combos = 1;
-        const size_t fixed = al16(sizeof(float) * (size_t)tcw::NCH * d) + al16(sizeof(double) * (size_t)NWARP * tcw::NCH) + sz_cs;
+        const size_t fixed = al16(sizeof(double) * (size_t)NWARP * tcw::NCH) + sz_cs;
         int nst = std::min(tcw::NST, 4 * a.nkc);
         if (const char* e = getenv("EPGPU_NST")) nst = std::max(2, std::min(nst, atoi(e)));
         while (nst >= 2 && al16(1024 + tcw::Smem::total(nst)) + fixed > budget) --nst;
         if (nst < 2 || nst < a.nkc) return false;
         a.tc_nst = nst;
         size_t o = al16(1024 + tcw::Smem::total(nst));
-        a.off_cavc = o; o += al16(sizeof(float) * (size_t)tcw::NCH * d);
         a.off_lp = o; o += al16(sizeof(double) * (size_t)NWARP * tcw::NCH);
         a.off_cs = o; o += sz_cs;
         a.smem_total = place_tail(o);
@@ -2012,7 +2016,8 @@ int epg_upload_sites(epg_ctx* c, int model, int D, const int64_t* k_lim, const d
                                                CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             s->tc_ok = (r == CUDA_SUCCESS);
         }
-        if (s->tc_ok) EPG_CHECK(c, cudaMalloc((void**)&s->gout_w, sizeof(float) * (size_t)K * 2 * tcw::NCH * tcw::KWT));
+        if (s->tc_ok)        // wide pass scratch: gradient halves [K][2][32][256] + cavity terms [K][32][d]
+            EPG_CHECK(c, cudaMalloc((void**)&s->gout_w, sizeof(float) * (size_t)K * tcw::NCH * (2 * tcw::KWT + c->d)));
     }
     return 0;
 }
@@ -2082,6 +2087,7 @@ static int fill_args(epg_ctx* c, SamplerArgs& a, int C, int CP, int n_sites = 1,
     // tensor-core pass: 1 = D+1 <= 64 and <= 16 chains (chain vectors in shared memory), 2 = wide (D+1 <= 256, <= 32 chains)
     a.use_tc = (s->tc_ok && s->use_tc) ? ((s->nkc == 1 && C <= tc::NCH) ? 1 : (C <= tcw::NCH ? 2 : 0)) : 0;
     a.nkc = s->nkc; a.xm_stride = tc::KW * s->nkc; a.gout_w = s->gout_w;
+    a.cavc_g = a.use_tc == 2 ? s->gout_w + (size_t)c->K * 2 * tcw::NCH * tcw::KWT : nullptr;
     if (a.use_tc == 2) {
         if (!plan_smem(a, CP, s->max_rows, c->d)) { a.use_tc = 0; }
         else return 0;

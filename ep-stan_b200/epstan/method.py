@@ -99,7 +99,10 @@ class Worker(object):
         'iter'            : 1000,
         'warmup'          : None,
         'thin'            : 1,
-        'init'            : 'random'
+        'init'            : 'random',
+        # extension (PyStan's own `sampling` keyword, which the reference never sets): NUTS controls of the
+        # built-in sampler, {'max_treedepth': int, 'adapt_delta': float}; None = Stan's defaults (10, 0.8)
+        'control'         : None
     }
 
     PREC_ESTIM_OPTIONS = ('sample', 'olse')
@@ -160,6 +163,9 @@ class Worker(object):
                     self.stan_params['thin']))
             if self.stan_params['init'] not in ('random', '0', 0):
                 raise ValueError("built-in sampler supports init 'random' or '0' only")
+            ctl = self.stan_params['control']
+            if ctl is not None and (not isinstance(ctl, dict) or set(ctl) - {'max_treedepth', 'adapt_delta'}):
+                raise ValueError("built-in sampler: `control` may hold 'max_treedepth' and 'adapt_delta' only")
         self.init_prev = options['init_prev']
         self.adapt_prev = bool(options['adapt_prev'])
         self.init_orig = self.stan_params['init']
@@ -209,6 +215,8 @@ class Worker(object):
         (the reference's in-process branch, method.py:369-397)."""
         t0 = time.perf_counter()
         params = dict(self.stan_params, seed=seed_stan, refresh=-1)
+        if params.get('control') is None:
+            params.pop('control', None)            # (the reference never passes it)
         fit = self.stan_model.sampling(data=self.data, **params)
         self.last_time = time.perf_counter() - t0
         self.last_msteps = float(np.mean([np.mean(p['stepsize__']) for p in fit.get_sampler_params()]))
@@ -260,7 +268,8 @@ class Worker(object):
         if self.builtin:
             sp = self.stan_params
             msteps, mrhat, nleap, secs = ctx.tilted_sample(
-                [seed_stan], sp['chains'], sp['iter'], sp['warmup'], self._init_mode(), kl, kl + 1)
+                [seed_stan], sp['chains'], sp['iter'], sp['warmup'], self._init_mode(), kl, kl + 1,
+                **(sp['control'] or {}))
             self.last_time, self.last_msteps, self.last_mrhat = secs, float(msteps[0]), float(mrhat[0])
             self.last_n_leapfrog = int(nleap[0])
             self._have_prev = True
@@ -772,7 +781,7 @@ class Master(object):
             if len(modes) != 1:
                 raise RuntimeError("sites disagree on the initialisation mode")
             msteps, mrhat, nleap, secs = ctx.tilted_sample(
-                stan_seeds, sp['chains'], sp['iter'], sp['warmup'], modes.pop())
+                stan_seeds, sp['chains'], sp['iter'], sp['warmup'], modes.pop(), **(sp['control'] or {}))
             for i, w in enumerate(workers):
                 w.last_time, w.last_msteps, w.last_mrhat = secs, float(msteps[i]), float(mrhat[i])
                 w.last_n_leapfrog = int(nleap[i])
