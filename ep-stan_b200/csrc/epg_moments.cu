@@ -371,7 +371,7 @@ namespace mm {
 constexpr int TCH = 32;            // draws per stage
 constexpr int PITCH = 36;          // doubles per stage row (== 4 mod 16: conflict-free fragment loads)
 constexpr int TB = 4;              // blocks per tile edge
-constexpr int MAX_TILES = 16;
+constexpr int MAX_TILES = 32;     // tiles of the lower triangle (d <= 200: 28), spread over `parts` CTAs per site
 
 __device__ __forceinline__ uint32_t s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -408,6 +408,8 @@ __device__ __forceinline__ void compute_sync(int nthreads) { asm volatile("bar.s
 
 struct Plan {                      // kernel parameter (host-built)
     int W, S, G, NS, rows;         // compute warps = G * S, stages, stage rows (8 * blocks)
+    int parts, Gtot, direct;       // CTAs per site (each owns G of the Gtot tiles and streams all the draws);
+                                   // direct: accumulators go straight to the global Gram slot (no smem copy; S == 1)
     int off_gram, off_vec, off_bar, off_stage, total;
     unsigned char ti[MAX_TILES], tj[MAX_TILES];      // tile (block-row / block-column index, in tiles) of every group
 };
@@ -427,7 +429,9 @@ __global__ void k_gram_mma(const double* __restrict__ draws, int n, int d, int k
     double* stage0 = reinterpret_cast<double*>(smem_raw + P.off_stage);
     const int stage_doubles = P.rows * PITCH;
     double* shiftaug = vec + 5 * d + 40;             // [rows]: 0, shift_0 .. shift_{d-1}, 0 ...
-    const double* x = draws + (size_t)(k0 + blockIdx.x) * d * n;
+    const int site = blockIdx.x / P.parts, part = blockIdx.x - site * P.parts;
+    const double* x = draws + (size_t)(k0 + site) * d * n;
+    double* G = gbuf + (size_t)site * gstride;
     const int nchunks = (n + TCH - 1) / TCH;
     const int ncomp = P.W * 32;
 
@@ -459,7 +463,9 @@ __global__ void k_gram_mma(const double* __restrict__ draws, int n, int d, int k
     } else if (warp < P.W) {
         // ===== compute: tile (ti, tj) of 4 x 4 blocks, draw slice `sl` =====
         const int grp = warp / P.S, sl = warp - grp * P.S;
-        const int bi0 = P.ti[grp] * TB, bj0 = P.tj[grp] * TB;
+        const int gidx = part * P.G + grp;          // this warp's tile; warps beyond the last tile only keep the ring moving
+        const bool owner = gidx < P.Gtot;
+        const int bi0 = owner ? P.ti[gidx] * TB : 0, bj0 = owner ? P.tj[gidx] * TB : 0;
         const int nblk = (da + 7) >> 3;             // blocks that hold data (the stage has rows for whole tiles)
         const bool diag = bi0 == bj0;
         double acc[TB][TB][2];
@@ -504,7 +510,8 @@ __global__ void k_gram_mma(const double* __restrict__ draws, int n, int d, int k
                     shb[i] = shiftaug[8 * (bj0 + i) + frow];
                 }
             }
-            if (tn == TCH) {
+            if (!owner) {
+            } else if (tn == TCH) {
                 for (int ks = sl; ks < TCH / 4; ks += P.S) kstep(sg, ks, true);
             } else {
                 for (int ks = sl; ks < TCH / 4; ks += P.S) kstep(sg, ks, 4 * ks + fcol < tn);
@@ -512,9 +519,10 @@ __global__ void k_gram_mma(const double* __restrict__ draws, int n, int d, int k
             __syncwarp();
             if (lane == 0) mbar_arrive(empty + st);
         }
-        // fixed-order sum over the draw slices into the packed Gram
+        // fixed-order sum over the draw slices into the packed Gram (direct: one slice, straight to global memory)
+        double* gdst = P.direct ? G : gram;
         for (int round = 0; round < P.S; ++round) {
-            if (sl == round) {
+            if (sl == round && owner) {
 #pragma unroll
                 for (int i = 0; i < TB; ++i)
 #pragma unroll
@@ -525,7 +533,7 @@ __global__ void k_gram_mma(const double* __restrict__ draws, int n, int d, int k
                             const int gi = 8 * (bi0 + i) + frow, gj = 8 * (bj0 + j) + 2 * fcol + e;
                             if (gi < da && gj <= gi) {
                                 const int idx = pk(gi, gj, da);
-                                gram[idx] = round == 0 ? acc[i][j][e] : gram[idx] + acc[i][j][e];
+                                gdst[idx] = round == 0 ? acc[i][j][e] : gdst[idx] + acc[i][j][e];
                             }
                         }
                     }
@@ -535,10 +543,9 @@ __global__ void k_gram_mma(const double* __restrict__ draws, int n, int d, int k
     }
     __syncthreads();
     // packed Gram (dimension d + 1) followed by the shift -> this site's slot of the scratch buffer
-    double* G = gbuf + (size_t)blockIdx.x * gstride;
     const int ng = pk_size(da);
-    for (int e = tid; e < ng; e += blockDim.x) G[e] = gram[e];
-    for (int e = tid; e < d; e += blockDim.x) G[ng + e] = shiftaug[1 + e];
+    if (!P.direct) for (int e = tid; e < ng; e += blockDim.x) G[e] = gram[e];
+    if (part == 0) for (int e = tid; e < d; e += blockDim.x) G[ng + e] = shiftaug[1 + e];
 }
 
 // ---- tail: the shared-memory factorisation / inversion on the Gram left by k_gram_mma ----
@@ -562,7 +569,7 @@ __global__ void k_moments_tail_smem(const double* __restrict__ gbuf, size_t gstr
 
 // host: tile plan of the DMMA kernel; returns false when the shape is left to the SIMT kernel
 static bool mma_plan(int d, int n, mm::Plan& P) {
-    if (d < 4 || d > 104 || (n & 1) || n < 8) return false;
+    if (d < 4 || d > 200 || (n & 1) || n < 8) return false;
     const int nblk = (d + 1 + 7) / 8;
     const int ntile = (nblk + mm::TB - 1) / mm::TB;
     int G = 0;
@@ -571,19 +578,26 @@ static bool mma_plan(int d, int n, mm::Plan& P) {
             if (G >= mm::MAX_TILES) return false;
             P.ti[G] = (unsigned char)ti; P.tj[G] = (unsigned char)tj; ++G;
         }
-    P.G = G;
-    P.S = G == 1 ? 4 : (G <= 3 ? 2 : 1);
+    P.Gtot = G;
+    // d <= 104 (<= 10 tiles): one CTA per site, Gram assembled in shared memory.  Larger d: the tiles are spread over
+    // `parts` CTAs per site (<= 14 compute warps each; every CTA streams all the draws, the second read hits L2) and
+    // the accumulators go straight to the site's global Gram slot -- the packed Gram (162 kB at d = 200) would not
+    // fit next to the stages
+    P.parts = G <= 10 ? 1 : (G + 13) / 14;
+    P.direct = P.parts > 1;
+    P.G = (G + P.parts - 1) / P.parts;
+    P.S = P.direct ? 1 : (G == 1 ? 4 : (G <= 3 ? 2 : 1));
     P.W = P.G * P.S;
     P.rows = 8 * mm::TB * ntile;                 // whole tiles: the padding rows hold zeros
     size_t o = 0;
-    P.off_gram = (int)o; o += sizeof(double) * (size_t)pk_size(d + 1);
+    P.off_gram = (int)o; if (!P.direct) o += sizeof(double) * (size_t)pk_size(d + 1);
     P.off_vec = (int)o;  o += sizeof(double) * (size_t)(5 * d + 40 + P.rows);
     o = (o + 15) & ~(size_t)15;
     P.off_bar = (int)o;  o += 16 * 2 * 8;
     o = (o + 127) & ~(size_t)127;
     P.off_stage = (int)o;
     const size_t stage_bytes = sizeof(double) * (size_t)P.rows * mm::PITCH;
-    P.NS = (int)std::min<size_t>(4, ((o + 4 * stage_bytes <= 100 * 1024 ? 100 : 200) * 1024 - o) / stage_bytes);
+    P.NS = (int)std::min<size_t>(4, ((o + 4 * stage_bytes <= 100 * 1024 ? 100 : 220) * 1024 - o) / stage_bytes);
     if (P.NS < 2) return false;
     P.NS = std::min(P.NS, 8);
     o += stage_bytes * P.NS;
@@ -606,7 +620,7 @@ cudaError_t epg_launch_moments(epg_ctx* c, int k0, int k1, int n, int mode) {
         if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(k_gram_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, P.total);
         if (e != cudaSuccess) return e;
-        k_gram_mma<<<K, 32 * (P.W + 1), P.total, c->stream>>>(c->draws, n, d, k0, c->mom_buf, gstride, P);
+        k_gram_mma<<<K * P.parts, 32 * (P.W + 1), P.total, c->stream>>>(c->draws, n, d, k0, c->mom_buf, gstride, P);
         c->launches++;
         const bool olse = mode == EPG_PREC_OLSE;
 #define EPG_TAIL_ARGS c->mom_buf, gstride, n, d, k0, c->arr[EPG_Q], c->arr[EPG_R], c->arr[EPG_DQI], c->arr[EPG_DRI], \

@@ -252,7 +252,8 @@ int epg_get_adapt(epg_ctx* ctx, int k, float* minv_out, float* eps_out);
  * and step size the previous run of the same chain ended with, instead of Stan's unit metric and step size 1
  * (an extension in the spirit of init_prev, method.py:404-406; the warm-up itself -- dual averaging, variance
  * windows -- still runs in full); 0 = Stan's defaults.  "use_tc" (default 1): use the tcgen05/TMA likelihood pass when the
- * shapes allow it (single-group sites, D+1 <= 64, chains <= 16); 0 forces the
+ * shapes allow it (single-group sites; D+1 <= 64 and chains <= 16: design matrix from L2, chain state in shared memory;
+ * otherwise D+1 <= 256 and chains <= 32: the wide pass, design matrix streamed from HBM -- config 5); 0 forces the
  * fp32 SIMT pass.  "pingpong" (default 0): 1 = with the tensor-core pass, more
  * sites than SMs and design matrices that stay L2-resident, run the persistent
  * two-sites-per-CTA kernel (likelihood pass of one site overlapped with the chain

@@ -161,7 +161,8 @@ def test_master_argument_errors(ep):
         == (0, (None, None))
 
 
-@pytest.mark.parametrize('K,d,n', [(64, 20, 800), (1024, 50, 800), (16, 200, 3200), (5, 7, 30), (3, 1, 10)])
+@pytest.mark.parametrize('K,d,n', [(64, 20, 800), (1024, 50, 800), (16, 200, 3200), (5, 7, 30), (3, 1, 10),
+                                   (6, 120, 600), (5, 150, 640), (4, 199, 802)])  # DMMA Gram: one CTA (10 tiles), two CTAs (15, 28 tiles)
 def test_moments_and_update_full_size(ep, K, d, n):
     """BASELINE config shapes (2, 4, 5) and ragged small ones, driven through the
     batched C-ABI calls; every site compared with the oracle."""
