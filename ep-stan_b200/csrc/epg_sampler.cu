@@ -1977,6 +1977,10 @@ int epg_upload_sites(epg_ctx* c, int model, int D, const int64_t* k_lim, const d
     if (s->Jmax == 1 && D + 1 <= tcw::KWT) {
         s->nkc = (D + 1 + tc::KW - 1) / tc::KW;
         s->xb_pitch = s->nkc == 1 ? tc::KW : ((D + 1 + 15) / 16) * 16;
+        // D+1 < 57: dense rows (D+1 rounded up to 8 columns = 16 bytes); the box stays 64 columns wide, the rest is
+        // out of bounds = zero-filled without L2 traffic (the tile phase of the narrow pass is bound by L2 -> SM bytes)
+        if (s->nkc == 1 && getenv("EPGPU_XB_DENSE") && atoi(getenv("EPGPU_XB_DENSE")) != 0)
+            s->xb_pitch = std::min(tc::KW, ((D + 1 + 7) / 8) * 8);
         const int xm_stride = tc::KW * s->nkc;
         EPG_CHECK(c, cudaMalloc((void**)&s->Xb, sizeof(__nv_bfloat16) * (size_t)N * s->xb_pitch));
         // per-site column means (fp64 on the host, stored as fp32) the bf16 copy is centred on
