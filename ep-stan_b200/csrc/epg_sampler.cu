@@ -1977,10 +1977,9 @@ int epg_upload_sites(epg_ctx* c, int model, int D, const int64_t* k_lim, const d
     if (s->Jmax == 1 && D + 1 <= tcw::KWT) {
         s->nkc = (D + 1 + tc::KW - 1) / tc::KW;
         s->xb_pitch = s->nkc == 1 ? tc::KW : ((D + 1 + 15) / 16) * 16;
-        // D+1 < 57: dense rows (D+1 rounded up to 8 columns = 16 bytes); the box stays 64 columns wide, the rest is
-        // out of bounds = zero-filled without L2 traffic (the tile phase of the narrow pass is bound by L2 -> SM bytes)
-        if (s->nkc == 1 && getenv("EPGPU_XB_DENSE") && atoi(getenv("EPGPU_XB_DENSE")) != 0)
-            s->xb_pitch = std::min(tc::KW, ((D + 1 + 7) / 8) * 8);
+        // (measured and not adopted: dense rows for D+1 < 57 -- pitch D+1 rounded up to 8 columns, the rest of the
+        //  64-column box out of bounds -- cut the L2 -> SM bytes of a tile by 12 % (config 4) / 62 % (config 3) and
+        //  changed nothing: 26.9k vs 27.0k and 13.6k vs 13.3k cycles per pass; the tile phase is not bound by L2 bytes)
         const int xm_stride = tc::KW * s->nkc;
         EPG_CHECK(c, cudaMalloc((void**)&s->Xb, sizeof(__nv_bfloat16) * (size_t)N * s->xb_pitch));
         // per-site column means (fp64 on the host, stored as fp32) the bf16 copy is centred on
