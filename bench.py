@@ -3,7 +3,12 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
                     [--workload cfg3|cfg4|cfg5|cfg1like] [--sites K] [--chains C] [--siter I]
-                    [--damp auto|schedule] [--data sim|synth]
+                    [--damp auto|schedule] [--data sim|synth] [--max-treedepth T] [--rhat-max R]
+
+    python bench.py --workload cfg5 --sites 148 --siter 100 --max-treedepth 6 --rhat-max 0 --no-cpu-baseline
+        BASELINE.json configs[4] (K=256, n_k=200 000, D=199, 32 chains), bounded: one wave of sites, 100
+        sampling iterations, tree depth <= 6 (a full-depth transition streams the site's 83 MB design matrix
+        1023 times); `roofline.bound` is "hbm" there (the wide tcgen05 pass streams X from HBM).
 
 A "step" is one full EP iteration over all K sites: tilted NUTS sampling of
 every site x chain (all draws), moment matching, damping selection, damped
