@@ -24,7 +24,8 @@ PATH = os.path.join(HERE, 'golden', 'nuts_ref.npz')
 # (model, J, n, D) of test_gpu_sampler.py::test_sampler_vs_oracle_nuts (site seed 21)
 SAMPLER_CASES = [('m1b', 1, 300, 4), ('m3b', 1, 400, 3), ('m4b', 2, 300, 3), ('m1b', 5, 250, 6),
                  ('m2b', 3, 300, 4), ('m5b', 1, 300, 3), ('m1b', 1, 600, 70),
-                 ('m1b', 1, 2000, 19)]       # BASELINE config-3 site shape (4 min of CPU)
+                 ('m1b', 1, 2000, 19), ('m3b', 1, 5000, 49)]       # BASELINE site shapes: 4 min / 55 min of CPU
+#                  (tools: the chains of one case can run in parallel processes, RandomState([seed, chain]))
 EP_MODELS = ['m1b', 'm4b']
 _cache = None
 

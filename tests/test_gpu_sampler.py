@@ -156,7 +156,7 @@ def _moment_check(draws_gpu, per_chain_gpu, ref):
                                            # wide tensor-core pass: > 16 chains (one sub-tile), D+1 > 64 (two)
                                            ('m1b', 1, 300, 4, 24), ('m1b', 1, 600, 70, 32),
                                            # BASELINE site shapes (configs 3 and 4) on the tensor-core pass
-                                           ('m1b', 1, 2000, 19, 8)])
+                                           ('m1b', 1, 2000, 19, 8), ('m3b', 1, 5000, 49, 4)])
 def test_sampler_vs_oracle_nuts(model, J, n, D, C):
     site = synth.make_site(model, n, D, J, seed=21)
     NS = 6
